@@ -1,0 +1,117 @@
+"""ctypes binding of libhmvae_b200.so (the C ABI in include/hmvae_b200.h).
+
+The library is the product: if it is missing or cannot be loaded, importing this module raises -- there is no
+PyTorch/CPU fallback anywhere in the package.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_longlong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhmvae_b200.so")
+
+
+class HmvaeError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    if os.environ.get("HMVAE_AUTOBUILD", "1") == "1":
+        from . import build as _build
+
+        _build.build()
+    else:
+        raise HmvaeError("libhmvae_b200.so is missing: run `python -m hm_vae_b200.build` (nvcc, sm_100a)")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+
+class ConvDesc(Structure):
+    _fields_ = [(n, c_int) for n in ("joints", "ci", "co", "ksize", "stride", "pad", "pad_mode", "upsample", "src_joints",
+                                     "lrelu", "out_joint_stride", "out_chan_offset", "out_channels_last")]
+
+
+class AdamTensor(Structure):
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("numel", c_long)]
+
+
+P = c_void_p
+IP = POINTER(c_int)
+_SIGS = {
+    "hmvae_last_error": (c_char_p, []),
+    "hmvae_version": (c_int, []),
+    "hmvae_launch_count": (c_longlong, []),
+    "hmvae_conv_plan_create": (c_int, [POINTER(ConvDesc), IP, IP, IP, POINTER(c_void_p)]),
+    "hmvae_conv_plan_destroy": (None, [c_void_p]),
+    "hmvae_conv_fprop": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
+    "hmvae_conv_dgrad": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
+    "hmvae_conv_wgrad": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "hmvae_conv_prologue_bwd": (c_int, [P, P, P, P, c_int, c_int, P]),
+    "hmvae_pool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, IP, IP, c_int, P]),
+    "hmvae_pool_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, IP, IP, c_int, P]),
+    "hmvae_unpool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, IP, P]),
+    "hmvae_unpool_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, IP, P]),
+    "hmvae_upsample2_fwd": (c_int, [P, P, c_long, c_int, P]),
+    "hmvae_upsample2_bwd": (c_int, [P, P, c_long, c_int, P]),
+    "hmvae_lrelu_fwd": (c_int, [P, P, c_long, c_float, P]),
+    "hmvae_lrelu_bwd": (c_int, [P, P, P, c_long, c_float, P]),
+    "hmvae_transpose_ct": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "hmvae_fk_fwd": (c_int, [P, c_int, P, P, IP, c_int, c_long, P, P, P]),
+    "hmvae_fk_bwd": (c_int, [P, c_int, P, P, IP, c_int, c_long, P, P, P, P]),
+    "hmvae_rot6d_fwd": (c_int, [P, P, c_long, P]),
+    "hmvae_rot6d_bwd": (c_int, [P, P, P, c_long, P]),
+    "hmvae_aa2rot_fwd": (c_int, [P, P, c_long, P]),
+    "hmvae_latent_fwd": (c_int, [P, P, P, P, c_long, c_int, P]),
+    "hmvae_latent_bwd": (c_int, [P, P, P, P, P, c_long, c_int, c_float, P]),
+    "hmvae_recon_fwdbwd": (c_int, [P, c_int, P, P, P, IP, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P]),
+    "hmvae_mse_fwd": (c_int, [P, P, P, c_long, P]),
+    "hmvae_mse_bwd": (c_int, [P, P, P, c_long, c_float, P]),
+    "hmvae_traj_fwdbwd": (c_int, [P, P, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, c_float, c_float, P, P, P]),
+    "hmvae_adam_step": (c_int, [POINTER(AdamTensor), c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
+}
+EXPORTS = sorted(_SIGS)
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)     # AttributeError here == the header and the library disagree
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib.hmvae_last_error()
+        raise HmvaeError("%s failed (code %d): %s" % (what or "hmvae call", rc, msg.decode() if msg else "?"))
+
+
+def int_array(values):
+    return (c_int * len(values))(*[int(v) for v in values])
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32 CUDA tensor (None -> NULL).  CPU tensors are an error: no fallback."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise HmvaeError("hm_vae_b200 ops run on CUDA tensors only (got a %s tensor); there is no CPU fallback" % t.device)
+    if t.dtype != torch.float32:
+        raise HmvaeError("hm_vae_b200 ops need float32 tensors (got %s)" % t.dtype)
+    if not t.is_contiguous():
+        raise HmvaeError("hm_vae_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def aligned(t):
+    """Contiguous fp32 view with a 16-byte aligned base pointer (clones only when needed)."""
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def launch_count():
+    return int(lib.hmvae_launch_count())

@@ -1,0 +1,152 @@
+// C ABI for the skeleton-aware conv: plan construction (index tables) and implementation dispatch.
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace hmvae {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+int conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float* w, const float* bias, float* y, int B, int T,
+                  cudaStream_t st);
+bool conv_fprop_tc_supported(const hmvae_conv_plan* plan, int B, int T);
+}  // namespace hmvae
+
+using namespace hmvae;
+
+extern "C" const char* hmvae_last_error(void) { return g_err; }
+extern "C" int hmvae_version(void) { return 100; }
+extern "C" long long hmvae_launch_count(void) { return g_launches.load(); }
+
+extern "C" int hmvae_conv_plan_create(const hmvae_conv_desc* desc, const int* nb_off, const int* nb_idx,
+                                      const int* unpool_src, hmvae_conv_plan** out) {
+  if (!desc || !nb_off || !nb_idx || !out) return fail_arg("conv_plan_create: null pointer");
+  const hmvae_conv_desc& d = *desc;
+  if (d.joints < 1 || d.joints > 64 || d.ci < 1 || d.co < 1) return fail_arg("conv_plan_create: bad joints/channels");
+  if (d.ksize < 1 || d.ksize > 32) return fail_arg("conv_plan_create: kernel_size must be in [1, 32]");
+  if (d.stride < 1 || d.stride > 2) return fail_arg("conv_plan_create: stride must be 1 or 2");
+  if (d.pad < 0 || (d.pad_mode != 0 && d.pad_mode != 1)) return fail_arg("conv_plan_create: bad padding");
+  const int J = d.joints, nnz = nb_off[J];
+  if (nb_off[0] != 0 || nnz < 0 || nnz > J * J) return fail_arg("conv_plan_create: bad neighbour CSR");
+  const int src_J = unpool_src ? d.src_joints : J;
+  if (src_J < 1 || src_J > 64) return fail_arg("conv_plan_create: bad src_joints");
+  hmvae_conv_plan* p = new hmvae_conv_plan();
+  p->d = d;
+  p->nb_off.assign(nb_off, nb_off + J + 1);
+  p->nb_idx.assign(nb_idx, nb_idx + nnz);
+  p->src.resize(J);
+  p->max_nb = 0;
+  for (int j = 0; j < J; ++j) {
+    p->src[j] = unpool_src ? unpool_src[j] : j;
+    if (p->src[j] < 0 || p->src[j] >= src_J) { delete p; return fail_arg("conv_plan_create: unpool source out of range"); }
+    if (nb_off[j + 1] < nb_off[j]) { delete p; return fail_arg("conv_plan_create: bad neighbour CSR"); }
+    if (nb_off[j + 1] - nb_off[j] > p->max_nb) p->max_nb = nb_off[j + 1] - nb_off[j];
+    for (int m = nb_off[j]; m < nb_off[j + 1]; ++m)
+      if (nb_idx[m] < 0 || nb_idx[m] >= J) { delete p; return fail_arg("conv_plan_create: neighbour out of range"); }
+  }
+  // transpose adjacency + block list
+  std::vector<int> tOff(J + 1, 0), tIdx(nnz), bj(nnz), bn(nnz);
+  for (int m = 0; m < nnz; ++m) tOff[nb_idx[m] + 1]++;
+  for (int j = 0; j < J; ++j) tOff[j + 1] += tOff[j];
+  std::vector<int> fill(J, 0);
+  for (int j = 0; j < J; ++j)
+    for (int m = nb_off[j]; m < nb_off[j + 1]; ++m) {
+      const int n = nb_idx[m];
+      tIdx[tOff[n] + fill[n]++] = j;
+      bj[m] = j;
+      bn[m] = n;
+    }
+  std::vector<int> host;
+  auto push = [&](const std::vector<int>& v) { size_t o = host.size(); host.insert(host.end(), v.begin(), v.end()); while (host.size() % 4) host.push_back(0); return o; };
+  const size_t o_nb_off = push(p->nb_off), o_nb_idx = push(p->nb_idx), o_t_off = push(tOff), o_t_idx = push(tIdx);
+  const size_t o_bj = push(bj), o_bn = push(bn), o_src = push(p->src);
+  cudaError_t e = cudaMalloc(&p->dev_tables, host.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(p->dev_tables, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "hmvae: conv_plan_create: %s", cudaGetErrorString(e));
+    delete p;
+    return (int)e;
+  }
+  ConvArgs& a = p->a;
+  a.J = J; a.ci = d.ci; a.co = d.co; a.K = d.ksize; a.s = d.stride; a.p = d.pad; a.pad_mode = d.pad_mode;
+  a.upsample = d.upsample ? 1 : 0; a.src_J = src_J; a.lrelu = d.lrelu ? 1 : 0;
+  a.ojs = d.out_joint_stride > 0 ? d.out_joint_stride : d.co;
+  a.oco = d.out_chan_offset; a.cl = d.out_channels_last ? 1 : 0; a.nnz = nnz;
+  if (a.ojs < a.oco + a.co) { cudaFree(p->dev_tables); delete p; return fail_arg("conv_plan_create: out_joint_stride too small"); }
+  a.nb_off = p->dev_tables + o_nb_off; a.nb_idx = p->dev_tables + o_nb_idx;
+  a.nbT_off = p->dev_tables + o_t_off; a.nbT_idx = p->dev_tables + o_t_idx;
+  a.blk_j = p->dev_tables + o_bj; a.blk_n = p->dev_tables + o_bn; a.src = p->dev_tables + o_src;
+  *out = p;
+  return 0;
+}
+
+extern "C" void hmvae_conv_plan_destroy(hmvae_conv_plan* plan) {
+  if (!plan) return;
+  cudaFree(plan->dev_tables);
+  delete plan;
+}
+
+static int check_shape(const hmvae_conv_plan* plan, int batch, int t_in, const char* who) {
+  if (!plan) { snprintf(g_err, sizeof(g_err), "hmvae: %s: null plan", who); return HMVAE_E_STATE; }
+  const hmvae_conv_desc& d = plan->d;
+  if (batch < 0 || t_in < 1) { snprintf(g_err, sizeof(g_err), "hmvae: %s: bad batch/time", who); return HMVAE_E_ARG; }
+  if (d.upsample && (t_in & 1)) { snprintf(g_err, sizeof(g_err), "hmvae: %s: upsampled length must be even", who); return HMVAE_E_ARG; }
+  if (d.pad_mode == 1 && d.pad > t_in - 1) {
+    snprintf(g_err, sizeof(g_err), "hmvae: %s: reflect padding %d needs an input of at least %d frames (got %d)", who, d.pad, d.pad + 1, t_in);
+    return HMVAE_E_ARG;
+  }
+  if (t_in + 2 * d.pad < d.ksize) { snprintf(g_err, sizeof(g_err), "hmvae: %s: input shorter than the kernel", who); return HMVAE_E_ARG; }
+  return 0;
+}
+
+extern "C" int hmvae_conv_fprop(const hmvae_conv_plan* plan, const float* x, const float* w, const float* bias, float* y,
+                                int batch, int t_in, int impl, void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_fprop");
+  if (rc) return rc;
+  if (!x || !w || !y) return fail_arg("conv_fprop: null pointer");
+  if (batch == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 2 || (impl == 0 && conv_fprop_tc_supported(plan, batch, t_in))) {
+    if (!conv_fprop_tc_supported(plan, batch, t_in)) return fail_arg("conv_fprop: tcgen05 path does not support this shape");
+    return conv_fprop_tc(plan, x, w, bias, y, batch, t_in, st);
+  }
+  return conv_fprop_simt(plan, x, w, bias, y, batch, t_in, st);
+}
+
+extern "C" int hmvae_conv_dgrad(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* w, float* dxin,
+                                int batch, int t_in, int impl, void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_dgrad");
+  if (rc) return rc;
+  if (!dy || !w || !dxin || (plan->d.lrelu && !y)) return fail_arg("conv_dgrad: null pointer");
+  if (batch == 0) return 0;
+  (void)impl;
+  return conv_dgrad_simt(plan, dy, y, w, dxin, batch, t_in, (cudaStream_t)stream);
+}
+
+extern "C" int hmvae_conv_wgrad(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* y, float* dw,
+                                float* dbias, int batch, int t_in, int accumulate, int impl, void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_wgrad");
+  if (rc) return rc;
+  if (!x || !dy || !dw || (plan->d.lrelu && !y)) return fail_arg("conv_wgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const hmvae_conv_desc& d = plan->d;
+  if (!accumulate) {
+    HMVAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d.joints * d.co * d.joints * d.ci * d.ksize, st));
+    if (dbias) HMVAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)d.joints * d.co, st));
+  }
+  if (batch == 0) return 0;
+  (void)impl;
+  return conv_wgrad_simt(plan, x, dy, y, dw, dbias, batch, t_in, st);
+}

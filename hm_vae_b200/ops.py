@@ -1,0 +1,426 @@
+"""torch.autograd bridges over the C ABI (include/hmvae_b200.h).
+
+Every op here launches hand-written sm_100a kernels from libhmvae_b200.so on the current CUDA stream, on
+caller-owned fp32 tensors; outputs come from PyTorch's caching allocator.  There is no CPU path.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import check, int_array, lib, ptr, stream
+
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+_conv_impl = IMPL_AUTO
+
+
+def set_conv_impl(impl):
+    """0 = auto, 1 = CUDA-core fp32, 2 = tcgen05 TF32 (parity tests pin one or the other)."""
+    global _conv_impl
+    _conv_impl = int(impl)
+
+
+# ------------------------------------------------------------------------------------------------ conv plan
+class ConvPlan:
+    """Immutable per-layer index tables on the device (neighbour CSR, transpose CSR, block list, unpool map)."""
+
+    def __init__(self, neighbour_list, ci, co, ksize, stride, pad, pad_mode, upsample=False, unpool_src=None,
+                 src_joints=None, lrelu=False, out_joint_stride=0, out_chan_offset=0, out_channels_last=False):
+        j = len(neighbour_list)
+        self.joints, self.ci, self.co, self.ksize, self.stride, self.pad = j, ci, co, ksize, stride, pad
+        self.pad_mode = {"constant": 0, "zeros": 0, "reflect": 1, "reflection": 1}[pad_mode]
+        self.upsample, self.lrelu = bool(upsample), bool(lrelu)
+        self.src_joints = int(src_joints) if unpool_src is not None else j
+        self.out_joint_stride = out_joint_stride or co
+        self.out_chan_offset = out_chan_offset
+        self.out_channels_last = bool(out_channels_last)
+        self.has_prologue = self.upsample or unpool_src is not None
+        off, idx = [0], []
+        for nb in neighbour_list:
+            idx.extend(int(k) for k in nb)
+            off.append(len(idx))
+        desc = _lib.ConvDesc(j, ci, co, ksize, stride, pad, self.pad_mode, int(self.upsample), self.src_joints,
+                             int(self.lrelu), self.out_joint_stride, out_chan_offset, int(self.out_channels_last))
+        handle = ctypes.c_void_p()
+        src = int_array(unpool_src) if unpool_src is not None else None
+        check(lib.hmvae_conv_plan_create(ctypes.byref(desc), int_array(off), int_array(idx), src, ctypes.byref(handle)),
+              "conv_plan_create")
+        self.handle = handle
+        self.device = torch.cuda.current_device()
+
+    def t_out(self, t_in):
+        return (t_in + 2 * self.pad - self.ksize) // self.stride + 1
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                lib.hmvae_conv_plan_destroy(h)
+            except Exception:
+                pass
+
+
+class _SkeletonConvFn(Function):
+    """y = epilogue(conv1d(pad(prologue(x)), W (.) mask, b)) -- skeleton.py:95-105 plus the fused neighbours."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, plan):
+        x = x.contiguous()
+        b, _, t_src = x.shape
+        t_in = t_src * 2 if plan.upsample else t_src
+        t_out = plan.t_out(t_in)
+        ctot = plan.joints * plan.out_joint_stride
+        shape = (b, t_out, ctot) if plan.out_channels_last else (b, ctot, t_out)
+        if plan.out_joint_stride != plan.co:
+            y = torch.zeros(shape, device=x.device, dtype=torch.float32)
+        else:
+            y = torch.empty(shape, device=x.device, dtype=torch.float32)
+        w = weight.contiguous()
+        check(lib.hmvae_conv_fprop(plan.handle, ptr(x), ptr(w), ptr(bias), ptr(y), b, t_in, _conv_impl, stream()), "conv_fprop")
+        ctx.plan, ctx.t_in, ctx.has_bias = plan, t_in, bias is not None
+        ctx.save_for_backward(x, w, y if plan.lrelu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        plan, t_in = ctx.plan, ctx.t_in
+        gy = gy.contiguous()
+        b = x.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            cin = plan.joints * plan.ci
+            gxin = torch.empty((b, cin, t_in), device=x.device, dtype=torch.float32)
+            check(lib.hmvae_conv_dgrad(plan.handle, ptr(gy), ptr(y), ptr(w), ptr(gxin), b, t_in, _conv_impl, stream()), "conv_dgrad")
+            if plan.has_prologue:
+                gx = torch.empty_like(x)
+                check(lib.hmvae_conv_prologue_bwd(plan.handle, ptr(gxin), None, ptr(gx), b, t_in, stream()), "conv_prologue_bwd")
+            else:
+                gx = gxin
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw = torch.empty_like(w)
+            gb = torch.empty(plan.joints * plan.co, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+            check(lib.hmvae_conv_wgrad(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, _conv_impl, stream()),
+                  "conv_wgrad")
+        return gx, gw, gb, None
+
+
+def skeleton_conv(x, weight, bias, plan):
+    return _SkeletonConvFn.apply(x, weight, bias, plan)
+
+
+# ------------------------------------------------------------------------------------------------ pool / unpool
+class _PoolFn(Function):
+    @staticmethod
+    def forward(ctx, x, off, idx, c, lrelu):
+        x = x.contiguous()
+        b, ch, t = x.shape
+        e_in, e_out = ch // c, len(off) - 1
+        y = torch.empty((b, e_out * c, t), device=x.device, dtype=torch.float32)
+        check(lib.hmvae_pool_fwd(ptr(x), ptr(y), b, e_in, e_out, c, t, int_array(off), int_array(idx), int(lrelu), stream()), "pool_fwd")
+        ctx.meta = (off, idx, c, lrelu, e_in, e_out)
+        ctx.save_for_backward(y if lrelu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        off, idx, c, lrelu, e_in, e_out = ctx.meta
+        gy = gy.contiguous()
+        b, _, t = gy.shape
+        gx = torch.empty((b, e_in * c, t), device=gy.device, dtype=torch.float32)
+        check(lib.hmvae_pool_bwd(ptr(gy), ptr(y), ptr(gx), b, e_in, e_out, c, t, int_array(off), int_array(idx), int(lrelu), stream()),
+              "pool_bwd")
+        return gx, None, None, None, None
+
+
+def skeleton_pool(x, pooling_list, c, lrelu=False):
+    off, idx = [0], []
+    for members in pooling_list:
+        idx.extend(members)
+        off.append(len(idx))
+    return _PoolFn.apply(x, off, idx, c, lrelu)
+
+
+class _UnpoolFn(Function):
+    @staticmethod
+    def forward(ctx, x, src, c, e_in):
+        x = x.contiguous()
+        b, _, t = x.shape
+        e_out = len(src)
+        y = torch.empty((b, e_out * c, t), device=x.device, dtype=torch.float32)
+        check(lib.hmvae_unpool_fwd(ptr(x), ptr(y), b, e_in, e_out, c, t, int_array(src), stream()), "unpool_fwd")
+        ctx.meta = (src, c, e_in, e_out)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        src, c, e_in, e_out = ctx.meta
+        gy = gy.contiguous()
+        b, _, t = gy.shape
+        gx = torch.empty((b, e_in * c, t), device=gy.device, dtype=torch.float32)
+        check(lib.hmvae_unpool_bwd(ptr(gy), ptr(gx), b, e_in, e_out, c, t, int_array(src), stream()), "unpool_bwd")
+        return gx, None, None, None
+
+
+def skeleton_unpool(x, src, c, e_in):
+    return _UnpoolFn.apply(x, src, c, e_in)
+
+
+class _Upsample2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        t = x.shape[-1]
+        y = torch.empty(x.shape[:-1] + (2 * t,), device=x.device, dtype=torch.float32)
+        check(lib.hmvae_upsample2_fwd(ptr(x), ptr(y), x.numel() // t, t, stream()), "upsample2_fwd")
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = gy.contiguous()
+        t = gy.shape[-1] // 2
+        gx = torch.empty(gy.shape[:-1] + (t,), device=gy.device, dtype=torch.float32)
+        check(lib.hmvae_upsample2_bwd(ptr(gy), ptr(gx), gx.numel() // t, t, stream()), "upsample2_bwd")
+        return gx
+
+
+def upsample2_linear(x):
+    return _Upsample2Fn.apply(x)
+
+
+class _LReluFn(Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(lib.hmvae_lrelu_fwd(ptr(x), ptr(y), x.numel(), slope, stream()), "lrelu_fwd")
+        ctx.slope = slope
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = torch.empty_like(gy)
+        check(lib.hmvae_lrelu_bwd(ptr(gy), ptr(y), ptr(gx), gy.numel(), ctx.slope, stream()), "lrelu_bwd")
+        return gx, None
+
+
+def leaky_relu(x, slope=0.2):
+    return _LReluFn.apply(x, slope)
+
+
+def _transpose_raw(x):
+    x = x.contiguous()
+    b, c, t = x.shape
+    y = torch.empty((b, t, c), device=x.device, dtype=torch.float32)
+    check(lib.hmvae_transpose_ct(ptr(x), ptr(y), b, c, t, stream()), "transpose_ct")
+    return y
+
+
+class _TransposeFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _transpose_raw(x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _transpose_raw(gy)
+
+
+def transpose_ct(x):
+    """[B, C, T] -> [B, T, C] (contiguous, differentiable)."""
+    return _TransposeFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------ rotations / FK
+class _Rot6dFn(Function):
+    @staticmethod
+    def forward(ctx, x6):
+        x = _lib.aligned(x6)
+        m = x.numel() // 6
+        r = torch.empty(x.shape[:-1] + (3, 3), device=x.device, dtype=torch.float32)
+        check(lib.hmvae_rot6d_fwd(ptr(x), ptr(r), m, stream()), "rot6d_fwd")
+        ctx.save_for_backward(x)
+        return r
+
+    @staticmethod
+    def backward(ctx, gr):
+        (x,) = ctx.saved_tensors
+        gr = _lib.aligned(gr)
+        gx = torch.empty_like(x)
+        check(lib.hmvae_rot6d_bwd(ptr(x), ptr(gr), ptr(gx), x.numel() // 6, stream()), "rot6d_bwd")
+        return gx
+
+
+def rot6d_to_rotmat(x6):
+    return _Rot6dFn.apply(x6)
+
+
+class _FKFn(Function):
+    @staticmethod
+    def forward(ctx, rot, offsets, positions, parents):
+        rot = _lib.aligned(rot)
+        rot_dim = 6 if rot.shape[-1] == 6 else 9
+        n, j = rot.shape[0], rot.shape[1]
+        if positions is not None:
+            positions = _lib.aligned(positions)
+        pos = torch.empty((n, j, 3), device=rot.device, dtype=torch.float32)
+        check(lib.hmvae_fk_fwd(ptr(rot), rot_dim, ptr(offsets), ptr(positions), int_array(parents), j, n, ptr(pos), None, stream()),
+              "fk_fwd")
+        ctx.meta = (rot_dim, parents, n, j)
+        ctx.save_for_backward(rot, offsets, positions)
+        return pos
+
+    @staticmethod
+    def backward(ctx, gpos):
+        rot, offsets, positions = ctx.saved_tensors
+        rot_dim, parents, n, j = ctx.meta
+        if ctx.needs_input_grad[2]:
+            raise _lib.HmvaeError("ForwardKinematicsLayer: gradient w.r.t. the `positions` argument is not implemented")
+        gpos = _lib.aligned(gpos)
+        grot = torch.empty_like(rot)
+        check(lib.hmvae_fk_bwd(ptr(rot), rot_dim, ptr(offsets), ptr(positions), int_array(parents), j, n, ptr(gpos), None, ptr(grot),
+                               stream()), "fk_bwd")
+        return grot, None, None, None
+
+
+def forward_kinematics(rot, offsets, positions, parents):
+    return _FKFn.apply(rot, offsets, positions, parents)
+
+
+def angle_axis_to_rotation_matrix(angle_axis):
+    """[N,3] -> [N,4,4] (torchgeometry semantics; no autograd -- inference / preprocessing only)."""
+    aa = angle_axis.contiguous()
+    if aa.dim() != 2 or aa.shape[1] != 3:
+        raise ValueError("Input size must be a (*, 3) tensor. Got {}".format(tuple(aa.shape)))
+    out = torch.empty((aa.shape[0], 4, 4), device=aa.device, dtype=torch.float32)
+    check(lib.hmvae_aa2rot_fwd(ptr(aa), ptr(out), aa.shape[0], stream()), "aa2rot_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ VAE latent
+class _LatentFn(Function):
+    """z = eps*exp(lv/2)+mu and the KL row-sum (seq_two_hier_sa_vae.py:419-428); dist is [rows, 2d] = (mu | lv)."""
+
+    @staticmethod
+    def forward(ctx, dist, eps, d):
+        dist = dist.contiguous()
+        rows = dist.numel() // (2 * d)
+        z = torch.empty((rows, d), device=dist.device, dtype=torch.float32)
+        kl = torch.zeros((), device=dist.device, dtype=torch.float32)
+        check(lib.hmvae_latent_fwd(ptr(dist), ptr(eps), ptr(z), ptr(kl), rows, d, stream()), "latent_fwd")
+        ctx.d, ctx.rows = d, rows
+        ctx.save_for_backward(dist, eps)
+        return z, kl
+
+    @staticmethod
+    def backward(ctx, gz, gkl):
+        dist, eps = ctx.saved_tensors
+        gd = torch.empty_like(dist)
+        gz = gz.contiguous() if gz is not None else None
+        gkl = gkl.contiguous() if gkl is not None else torch.zeros((), device=dist.device)
+        check(lib.hmvae_latent_bwd(ptr(dist), ptr(eps), ptr(gz), ptr(gkl), ptr(gd), ctx.rows, ctx.d, 1.0, stream()), "latent_bwd")
+        return gd, None, None
+
+
+def latent_sample_kl(dist, eps, d):
+    """Returns (z [rows, d], kl_sum scalar).  kl mean = kl_sum / rows."""
+    return _LatentFn.apply(dist, eps, d)
+
+
+# ------------------------------------------------------------------------------------------------ MSE
+class _MseSumFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.zeros((), device=a.device, dtype=torch.float32)
+        check(lib.hmvae_mse_fwd(ptr(a), ptr(b), ptr(out), a.numel(), stream()), "mse_fwd")
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a)
+        check(lib.hmvae_mse_bwd(ptr(a), ptr(b), ptr(da), a.numel(), 2.0, stream()), "mse_bwd")
+        return da * g, None
+
+
+def l2_criterion(pred, gt):
+    """mean((pred-gt)^2) -- seq_two_hier_sa_vae.py:430-434 (gt gets no gradient)."""
+    assert pred.size() == gt.size()
+    return _MseSumFn.apply(pred, gt) / pred.numel()
+
+
+# ------------------------------------------------------------------------------------------------ fused losses / optimiser
+def recon_fwdbwd(x6_pred, ncw, gt_6d, gt_rotmat, offsets, parents, w6d, wrot, wpos, losses, want_grad=True):
+    """Fused GT-FK + rot6d + FK + 3 MSE (+ gradient w.r.t. x6_pred).  `losses` is a zeroed float32[>=3] device tensor
+    that receives the three squared-error SUMS.  Returns dx6 (same layout as x6_pred) or None."""
+    x6_pred = x6_pred.contiguous()
+    if ncw:
+        b, c, t = x6_pred.shape
+    else:
+        b, t, c = x6_pred.shape
+    j = c // 6
+    nf = float(b * t)
+    dx6 = torch.empty_like(x6_pred) if want_grad else None
+    check(lib.hmvae_recon_fwdbwd(ptr(x6_pred), int(ncw), ptr(_lib.aligned(gt_6d)), ptr(_lib.aligned(gt_rotmat)), ptr(offsets),
+                                 int_array(parents), j, b, t, 2.0 * w6d / (nf * 6 * j), 2.0 * wrot / (nf * 9 * j),
+                                 2.0 * wpos / (nf * 3 * j), ptr(losses), ptr(dx6), None, None, stream()), "recon_fwdbwd")
+    return dx6
+
+
+def traj_fwdbwd(root_v_pred, root_v_gt, mean3, std3, joints, w_v, w_trans, losses, want_grad=True):
+    root_v_pred, root_v_gt = root_v_pred.contiguous(), root_v_gt.contiguous()
+    b, t, _ = root_v_pred.shape
+    d = torch.empty_like(root_v_pred) if want_grad else None
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean3])
+    s = (ctypes.c_float * 3)(*[float(v) for v in std3])
+    check(lib.hmvae_traj_fwdbwd(ptr(root_v_pred), ptr(root_v_gt), m, s, b, t, joints, 2.0 * w_v / (b * t * 3),
+                                2.0 * w_trans / (t * b * joints * 3), ptr(losses), ptr(d), stream()), "traj_fwdbwd")
+    return d
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas, eps, weight_decay) semantics in one multi-tensor kernel (trainer_motion_vae.py:29-31)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params]
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.step_count = 0
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self.param_groups = [dict(lr=lr)]
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def step(self, grad_scale=1.0, lr=None, step=None):
+        self.step_count = self.step_count + 1 if step is None else step
+        live = [(p, m, v) for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq) if p.grad is not None]
+        arr = (_lib.AdamTensor * len(live))()
+        for i, (p, m, v) in enumerate(live):
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            arr[i] = _lib.AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
+        check(lib.hmvae_adam_step(arr, len(live), self.param_groups[0]["lr"] if lr is None else lr, self.betas[0], self.betas[1],
+                                  self.eps, self.weight_decay, self.step_count, grad_scale, stream()), "adam_step")
+
+    def state_dict(self):
+        return dict(step=self.step_count, lr=self.param_groups[0]["lr"], exp_avg=[m.clone() for m in self.exp_avg],
+                    exp_avg_sq=[v.clone() for v in self.exp_avg_sq])
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.param_groups[0]["lr"] = sd.get("lr", self.lr)
+        for m, s in zip(self.exp_avg, sd["exp_avg"]):
+            m.copy_(s)
+        for v, s in zip(self.exp_avg_sq, sd["exp_avg_sq"]):
+            v.copy_(s)

@@ -1,0 +1,170 @@
+/*
+ * hmvae_b200.h -- C ABI of the B200-native hm-vae hot path (libhmvae_b200.so).
+ *
+ * Plain pointers and sizes only; every pointer named `d_*` / documented "device" is a CUDA device
+ * pointer to contiguous fp32 (or int32) data, 16-byte aligned.  `stream` is a cudaStream_t passed as
+ * void*.  Every entry point returns 0 on success, a negative HMVAE_E_* code on argument errors and a
+ * positive cudaError_t on CUDA failures; hmvae_last_error() returns a thread-local message.
+ * There is NO CPU fallback: a build without the CUDA kernels does not exist.
+ *
+ * Each entry replaces a PyTorch call chain of the reference (file:line into lijiaman/hm-vae):
+ *
+ *   hmvae_conv_*            skeleton.py:95-105      SkeletonConv.forward  (weight*mask, F.pad, F.conv1d) + autograd
+ *   hmvae_pool_* / unpool   skeleton.py:228-231, 258-261   SkeletonPool/Unpool.forward (matmul by 0/.5/1 matrix)
+ *   hmvae_upsample2_*       seq_two_hier_sa_vae.py:233-240 nn.Upsample(x2, linear, align_corners=False)
+ *   hmvae_lrelu_*           seq_two_hier_sa_vae.py:129,256 nn.LeakyReLU(0.2)
+ *   hmvae_fk_*              fk_layer.py:47-93       ForwardKinematicsLayer.forward (+ my_tools 6D input path)
+ *   hmvae_rot6d_*           my_tools.py:19-39       rotation_matrix_from_ortho6d
+ *   hmvae_aa2rot_fwd        torchgeometry.angle_axis_to_rotation_matrix (call site seq_two_hier_sa_vae.py:650)
+ *   hmvae_latent_*          seq_two_hier_sa_vae.py:419-428  reparametrize + kl_loss
+ *   hmvae_recon_fwdbwd      seq_two_hier_sa_vae.py:343, 441-468, 395-411  GT FK, rot6d->R, FK, 3x MSE and their backward
+ *   hmvae_mse_*             seq_two_hier_sa_vae.py:430-434  l2_criterion
+ *   hmvae_traj_*            trajectory_pred_model.py:289-303, 237-244  gen_motion_w_trajectory + 2x MSE
+ *   hmvae_adam_step         trainer_motion_vae.py:29-31, 92-93  torch.optim.Adam(lr, weight_decay) step
+ */
+#ifndef HMVAE_B200_H
+#define HMVAE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMVAE_E_ARG (-1)     /* bad argument (shape, alignment, unsupported mode) */
+#define HMVAE_E_STATE (-2)   /* bad handle */
+
+const char* hmvae_last_error(void);
+int hmvae_version(void);
+/* Number of kernels this library has launched in the calling process (all threads). */
+long long hmvae_launch_count(void);
+
+/* ------------------------------------------------------------------ skeleton-aware conv */
+
+typedef struct hmvae_conv_plan hmvae_conv_plan;
+
+/* Layer geometry + fused prologue/epilogue.  Channel index = joint * channels_per_joint + c on both sides. */
+typedef struct {
+  int joints;        /* J: edges at this level (in == out) */
+  int ci, co;        /* channels per joint, input / output */
+  int ksize;         /* K taps */
+  int stride;        /* 1 or 2 */
+  int pad;           /* zeros/reflect padding on both sides */
+  int pad_mode;      /* 0 = zeros ('constant'), 1 = reflect */
+  /* prologue (decoder): conv input = unpool(upsample2(src)) -- both optional */
+  int upsample;      /* 1: src has T/2 frames, x2 linear upsample (align_corners=False) is applied on the fly */
+  int src_joints;    /* joints of src tensor when unpool_src != NULL, else == joints */
+  /* epilogue */
+  int lrelu;         /* 1: LeakyReLU(0.2) on the output */
+  int out_joint_stride; /* channels between consecutive output joints in y (>= co; == co for a plain tensor) */
+  int out_chan_offset;  /* first channel inside each output joint block (for writing into a concat buffer) */
+  int out_channels_last;/* 1: y is [B, T_out, J*co] instead of [B, J*co, T_out] */
+} hmvae_conv_desc;
+
+/* neighbours: CSR (nb_off[J+1], nb_idx[nnz]) host arrays, skeleton.py:34-39.  unpool_src: host [J] or NULL. */
+int hmvae_conv_plan_create(const hmvae_conv_desc* desc, const int* nb_off, const int* nb_idx,
+                           const int* unpool_src, hmvae_conv_plan** out);
+void hmvae_conv_plan_destroy(hmvae_conv_plan* plan);
+
+/* y[B, J*co, T_out] = epilogue(conv1d(pad(prologue(x)), W (.) mask, bias, stride)).
+ * x: [B, src_joints*ci, T_src], w: dense [J*co, J*ci, K] (masked entries are never read), bias may be NULL.
+ * T is the conv-input length (T_src*2 when upsample).  impl: 0 = auto, 1 = CUDA-core fp32, 2 = tcgen05 TF32. */
+int hmvae_conv_fprop(const hmvae_conv_plan* plan, const float* x, const float* w, const float* bias, float* y,
+                     int batch, int t_in, int impl, void* stream);
+/* dxin[B, J*ci, T]: gradient w.r.t. the *virtual* conv input (after unpool/upsample, before padding); the
+ * padding adjoint is folded in.  If the plan has lrelu, dy is first multiplied by lrelu'(y) using y. */
+int hmvae_conv_dgrad(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* w, float* dxin,
+                     int batch, int t_in, int impl, void* stream);
+/* dw: dense [J*co, J*ci, K]; only unmasked blocks are written (masked entries keep their previous value,
+ * which must be 0).  dbias may be NULL.  accumulate != 0 adds into dw/dbias. */
+int hmvae_conv_wgrad(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* y, float* dw,
+                     float* dbias, int batch, int t_in, int accumulate, int impl, void* stream);
+/* adjoint of the prologue: dsrc[B, src_joints*ci, T_src] from dxin[B, J*ci, T]; if src_act != NULL the result is
+ * multiplied by lrelu'(src_act) (src_act = the activation tensor that fed this layer). */
+int hmvae_conv_prologue_bwd(const hmvae_conv_plan* plan, const float* dxin, const float* src_act, float* dsrc,
+                            int batch, int t_in, void* stream);
+
+/* ------------------------------------------------------------------ pool / unpool / upsample / lrelu */
+
+/* pooling table: CSR over output edges (host arrays, <= 64 edges).  y = mean over members (skeleton.py:219-226). */
+int hmvae_pool_fwd(const float* x, float* y, int batch, int in_edges, int out_edges, int c, int t,
+                   const int* pool_off, const int* pool_idx, int lrelu, void* stream);
+/* dx = pool^T(dy (.) lrelu'(y)) ; y may be NULL when lrelu == 0 */
+int hmvae_pool_bwd(const float* dy, const float* y, float* dx, int batch, int in_edges, int out_edges, int c, int t,
+                   const int* pool_off, const int* pool_idx, int lrelu, void* stream);
+/* unpool: y[:, j*c + ch] = x[:, src[j]*c + ch] (skeleton.py:248-256); bwd sums over members. */
+int hmvae_unpool_fwd(const float* x, float* y, int batch, int in_edges, int out_edges, int c, int t, const int* src,
+                     void* stream);
+int hmvae_unpool_bwd(const float* dy, float* dx, int batch, int in_edges, int out_edges, int c, int t, const int* src,
+                     void* stream);
+int hmvae_upsample2_fwd(const float* x, float* y, long rows, int t, void* stream);
+int hmvae_upsample2_bwd(const float* dy, float* dx, long rows, int t, void* stream);
+int hmvae_lrelu_fwd(const float* x, float* y, long n, float slope, void* stream);
+int hmvae_lrelu_bwd(const float* dy, const float* y, float* dx, long n, float slope, void* stream);
+/* [B, C, T] <-> [B, T, C] */
+int hmvae_transpose_ct(const float* x, float* y, int batch, int c, int t, void* stream);
+
+/* ------------------------------------------------------------------ rotations / forward kinematics */
+
+/* rot: [N, J, 3, 3] (rot_dim 9) or [N, J, 6] (rot_dim 6).  offsets: device [J,3]; positions: device [N,J,3] or NULL
+ * (fk_layer.py:82-89).  parents: HOST int[J], parents[0] ignored, parents[i] < i required.  pos: [N, J, 3].
+ * rotmat_out (optional, rot_dim == 6 only): [N, J, 3, 3] = rot6d->R of the input. */
+int hmvae_fk_fwd(const float* rot, int rot_dim, const float* offsets, const float* positions, const int* parents,
+                 int joints, long n, float* pos, float* rotmat_out, void* stream);
+/* drot: [N, J, rot_dim].  drotmat_extra (optional, rot_dim == 6): extra upstream gradient on R, [N,J,3,3]. */
+int hmvae_fk_bwd(const float* rot, int rot_dim, const float* offsets, const float* positions, const int* parents,
+                 int joints, long n, const float* dpos, const float* drotmat_extra, float* drot, void* stream);
+int hmvae_rot6d_fwd(const float* x6, float* rotmat, long m, void* stream);
+int hmvae_rot6d_bwd(const float* x6, const float* drotmat, float* dx6, long m, void* stream);
+/* [M,3] -> [M,4,4] homogeneous (torchgeometry semantics, small-angle Taylor branch at theta^2 <= 1e-6) */
+int hmvae_aa2rot_fwd(const float* aa, float* out44, long m, void* stream);
+
+/* ------------------------------------------------------------------ fused VAE losses */
+
+/* z = eps*exp(0.5*lv)+mu, kl_sum += sum_rows(-0.5*sum_d(1+lv-mu^2-exp(lv))).  dist: [rows, 2*d] = (mu|lv).
+ * eps may be NULL (z = mu).  kl_out: device float[1], ATOMICALLY accumulated: caller zeroes it. */
+int hmvae_latent_fwd(const float* dist, const float* eps, float* z, float* kl_out, long rows, int d, void* stream);
+/* ddist = [dz + s*mu | dz*eps*0.5*exp(0.5 lv) + s*0.5*(exp(lv)-1)],  s = kl_scale * (dkl ? *dkl : 1).
+ * kl_scale = kl_w/rows for a fused loss; dkl is an optional DEVICE scalar (upstream gradient of the KL sum).
+ * dz may be NULL (detached z). */
+int hmvae_latent_bwd(const float* dist, const float* eps, const float* dz, const float* dkl, float* ddist, long rows,
+                     int d, float kl_scale, void* stream);
+
+/* One kernel for: GT FK (no grad), rot6d->R, FK on the prediction, the three MSEs and d(total)/d(x6_pred).
+ * x6_pred: decoder output, NCW [B, 24*6, T] (ncw=1) or [B, T, 24*6] (ncw=0); gt_6d [B,T,144]; gt_rotmat [B,T,216].
+ * losses: device float[4], ATOMICALLY accumulated (caller zeroes): {sum sq 6d, sum sq rot, sum sq pos, unused}.
+ * dx6 (may be NULL for validation): same layout as x6_pred, = w6d*2(d)/n6 + ... (weights already divided by the
+ * element counts by the caller: s6 = 2*w_6d/numel etc).  pos_pred_out / gt_pos_out optional [B,T,72]. */
+int hmvae_recon_fwdbwd(const float* x6_pred, int ncw, const float* gt_6d, const float* gt_rotmat,
+                       const float* offsets, const int* parents, int joints, int batch, int t,
+                       float s6, float srot, float spos, float* losses, float* dx6, float* pos_pred_out,
+                       float* gt_pos_out, void* stream);
+/* sum((a-b)^2) atomically added to out[0]; grad: da = scale*(a-b) */
+int hmvae_mse_fwd(const float* a, const float* b, float* out, long n, void* stream);
+int hmvae_mse_bwd(const float* a, const float* b, float* da, long n, float scale, void* stream);
+
+/* trajectory accumulation (prefix sum over T of de-standardised root velocity, added to every joint) + its MSE.
+ * root_v_pred/gt: [B,T,3] standardised; mean/std: 3 floats each (host); returns in losses[0] sum sq of
+ * (root_v_pred-root_v_gt), losses[1] sum sq of accumulated trajectories difference *per joint-coordinate*
+ * (already multiplied by the 24 joints); d_root_v = gradient of  sv*L_v + st*L_trans  (sv, st pre-divided). */
+int hmvae_traj_fwdbwd(const float* root_v_pred, const float* root_v_gt, const float* mean3, const float* std3,
+                      int batch, int t, int joints, float sv, float st, float* losses, float* d_root_v,
+                      void* stream);
+
+/* ------------------------------------------------------------------ optimiser */
+
+/* torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, eps outside sqrt):
+ *   g += wd*p; m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g*g; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * tensors: HOST array of n_tensors {p,g,m,v device pointers, numel}; grad_scale multiplies g first (1/world). */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long numel;
+} hmvae_adam_tensor;
+int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

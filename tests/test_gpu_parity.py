@@ -1,0 +1,378 @@
+"""GPU parity: the sm_100a kernels (through the C ABI / module surface) against the oracle and the golden vectors.
+
+Tolerances: fp32 FK / rotations 1e-5 relative (abs floor 1e-5 on O(1) values); fp32 CUDA-core conv 1e-4 relative-L2;
+TF32 tensor-core conv and losses 2e-3 (relative-L2 for tensors, relative for scalars) -- BASELINE.json north_star.
+"""
+import numpy as np
+import pytest
+import torch
+
+import hm_vae_b200 as H
+from hm_vae_b200 import ops
+from hm_vae_b200.seq_two_hier_sa_vae import TwoHierSAVAEModel
+from hm_vae_b200.trajectory_pred_model import TrajectoryModel
+from oracle import hmvae_ref as O
+from test_oracle_golden import HP64, HP8, HPT, _cks
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def cu(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float32).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def fk(smpl):
+    return H.ForwardKinematicsLayer(device=torch.device(DEV), parents=smpl["parents"].tolist(), positions=smpl["offsets"])
+
+
+# ------------------------------------------------------------------------------------------------ rotations / FK
+def test_fk_identity_is_rest_pose(fk, smpl):
+    for n in (1, 31, 32, 33, 1000):
+        eye = torch.eye(3, device=DEV)[None, None].repeat(n, 24, 1, 1)
+        pos = fk(eye)
+        assert pos.shape == (n, 24, 3)
+        assert np.abs(pos.cpu().numpy() - smpl["rest_pose"][None]).max() < 1e-6
+
+
+def test_rot6d_golden(golden_modules):
+    g = golden_modules
+    x = cu(g["rot6d_x"]).requires_grad_(True)
+    r = H.rotation_matrix_from_ortho6d(x)
+    ok = np.ones((5, 24), bool)
+    ok[2, 5] = False
+    np.testing.assert_allclose(r.detach().cpu().numpy()[ok], g["rot6d_R"][ok], atol=2e-6)
+    assert float(r[1, 3].abs().max()) == 0.0 and not torch.isnan(r).any()
+    r.backward(cu(g["rot6d_gR"]))
+    np.testing.assert_allclose(x.grad.cpu().numpy()[ok], g["rot6d_gx"][ok], rtol=1e-4, atol=1e-5)
+    assert not torch.isnan(x.grad).any()
+
+
+def test_fk_golden_fwd_bwd(fk, golden_modules):
+    g = golden_modules
+    for tag, key_in, key_g in [("fk", "fk_R", "fk_gR"), ("fk2", "fk2_R", "fk2_gR"), ("fk6", "fk6_x", "fk6_gx")]:
+        rin = cu(g[key_in]).requires_grad_(True)
+        pos = fk(rin)
+        np.testing.assert_allclose(pos.detach().cpu().numpy(), g[tag + "_pos"], rtol=1e-5, atol=1e-5)
+        pos.backward(cu(g[tag + "_gpos"]))
+        np.testing.assert_allclose(rin.grad.cpu().numpy(), g[key_g], rtol=1e-4, atol=2e-5)
+    pos = fk(cu(g["fk2_R"]), cu(g["fkp_positions"]))
+    np.testing.assert_allclose(pos.cpu().numpy(), g["fkp_pos"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("n", [0, 1, 43, 683, 10923])
+@pytest.mark.parametrize("six", [False, True])
+def test_fk_vs_oracle_sweep(fk, smpl, n, six):
+    if n == 0:
+        out = fk(torch.zeros(0, 24, 6 if six else 3, *(() if six else (3,)), device=DEV))
+        assert out.shape == (0, 24, 3)
+        return
+    gen = torch.Generator().manual_seed(n)
+    x6 = torch.randn(n, 24, 6, generator=gen)
+    rot = x6 if six else O.rot6d_to_rotmat(x6)
+    gp = torch.randn(n, 24, 3, generator=gen)
+    ref_in = rot.clone().requires_grad_(True)
+    ref = O.forward_kinematics(ref_in, smpl["parents"], torch.from_numpy(smpl["offsets"]))
+    ref.backward(gp)
+    mine_in = rot.to(DEV).requires_grad_(True)
+    mine = fk(mine_in)
+    mine.backward(gp.to(DEV))
+    assert rel_l2(mine.detach().cpu(), ref.detach()) < 1e-5
+    assert rel_l2(mine_in.grad.cpu(), ref_in.grad) < 1e-5
+    np.testing.assert_allclose(mine.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_fk_generic_tree_vs_oracle():
+    parents = [-1, 0, 1, 1, 0, 4, 5, 5, 2, 8, 3]          # 11 joints: not SMPL, J % 4 != 0 -> generic kernel
+    gen = torch.Generator().manual_seed(5)
+    off = torch.randn(11, 3, generator=gen)
+    layer = H.ForwardKinematicsLayer(device=torch.device(DEV), parents=parents, positions=off.numpy())
+    for six in (False, True):
+        rot = torch.randn(77, 11, 6, generator=gen) if six else torch.randn(77, 11, 3, 3, generator=gen)
+        gp = torch.randn(77, 11, 3, generator=gen)
+        ref_in = rot.clone().requires_grad_(True)
+        ref = O.forward_kinematics(ref_in, parents, off)
+        ref.backward(gp)
+        mine_in = rot.to(DEV).requires_grad_(True)
+        mine = layer(mine_in)
+        mine.backward(gp.to(DEV))
+        assert rel_l2(mine.detach().cpu(), ref.detach()) < 1e-5
+        assert rel_l2(mine_in.grad.cpu(), ref_in.grad) < 2e-5
+
+
+def test_aa2rot_vs_oracle():
+    gen = torch.Generator().manual_seed(9)
+    aa = torch.randn(1000, 3, generator=gen)
+    aa[:10] *= 1e-4
+    mine = H.angle_axis_to_rotation_matrix(aa.to(DEV)).cpu()
+    ref = O.angle_axis_to_rotation_matrix(aa)
+    np.testing.assert_allclose(mine.numpy(), ref.numpy(), atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ conv / pool / unpool / upsample
+def _conv_case(g, topo, n):
+    lvl, ci, co, k, s, p, refl, bias, b, t = [int(v) for v in g[f"conv{n}_cfg"]]
+    nb = topo["levels"][lvl]["neighbours"]
+    conv = H.SkeletonConv(nb, len(nb) * ci, len(nb) * co, k, len(nb), stride=s, padding=p, bias=bool(bias),
+                          padding_mode="reflection" if refl else "zeros").to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(cu(g[f"conv{n}_w"]))
+        if bias:
+            conv.bias.copy_(cu(g[f"conv{n}_b"]))
+    return conv, bool(bias)
+
+
+@pytest.mark.parametrize("n", range(5))
+def test_conv_golden_simt(golden_modules, golden_topology, n):
+    g = golden_modules
+    ops.set_conv_impl(ops.IMPL_SIMT)
+    conv, bias = _conv_case(g, golden_topology, n)
+    x = cu(g[f"conv{n}_x"]).requires_grad_(True)
+    y = conv(x)
+    assert rel_l2(y.detach().cpu(), g[f"conv{n}_y"]) < 1e-5
+    y.backward(cu(g[f"conv{n}_gy"]))
+    assert rel_l2(x.grad.cpu(), g[f"conv{n}_gx"]) < 1e-5
+    assert rel_l2(conv.weight.grad.cpu(), g[f"conv{n}_gw"]) < 1e-5
+    assert float((conv.weight.grad * (1 - conv.mask)).abs().sum()) == 0.0      # masked entries stay exactly 0
+    if bias:
+        assert rel_l2(conv.bias.grad.cpu(), g[f"conv{n}_gb"]) < 1e-5
+    ops.set_conv_impl(ops.IMPL_AUTO)
+
+
+def test_pool_unpool_upsample_golden(golden_modules, golden_topology):
+    g = golden_modules
+    for lvl in range(4):
+        edges = [tuple(e) for e in golden_topology["levels"][lvl]["edges"]]
+        pool = H.SkeletonPool(edges, "mean", 3, last_pool=(lvl == 3)).to(DEV)
+        un = H.SkeletonUnpool(pool.pooling_list, 3).to(DEV)
+        x = cu(g[f"pool{lvl}_x"]).requires_grad_(True)
+        y = pool(x)
+        assert np.array_equal(y.detach().cpu().numpy(), g[f"pool{lvl}_y"])
+        z = un(y)
+        assert np.array_equal(z.detach().cpu().numpy(), g[f"unpool{lvl}_y"])
+        gz = torch.randn_like(z)
+        z.backward(gz)
+        ref = torch.matmul(pool.weight.t(), torch.matmul(un.weight.t(), gz))
+        assert rel_l2(x.grad.cpu(), ref.cpu()) < 1e-6
+    xu = cu(g["up_x"]).requires_grad_(True)
+    yu = ops.upsample2_linear(xu)
+    np.testing.assert_allclose(yu.detach().cpu().numpy(), g["up_y"], atol=1e-6)
+    gu = torch.randn_like(yu)
+    yu.backward(gu)
+    xr = torch.from_numpy(g["up_x"]).requires_grad_(True)
+    O.upsample2_linear(xr).backward(gu.cpu())
+    np.testing.assert_allclose(xu.grad.cpu().numpy(), xr.grad.numpy(), atol=1e-6)
+
+
+LAYER_SHAPES = [  # (level, ci, co, K, stride, T_in, upsample, unpool_level)  -- the 8 len64 convs + len8 / trajectory ones
+    (0, 6, 12, 15, 2, 64, False, None), (1, 12, 24, 15, 2, 32, False, None), (2, 24, 48, 15, 2, 16, False, None),
+    (3, 48, 96, 15, 2, 8, False, None), (3, 96, 48, 15, 1, 8, True, 3), (2, 48, 24, 15, 1, 16, True, 2),
+    (1, 24, 12, 15, 1, 32, True, 1), (0, 24, 6, 15, 1, 64, True, 0), (0, 6, 12, 3, 1, 8, False, None),
+    (0, 3, 6, 31, 1, 128, False, None), (3, 24, 48, 31, 1, 128, False, None),
+]
+
+
+@pytest.mark.parametrize("shape", LAYER_SHAPES)
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_conv_layer_shapes_vs_oracle(golden_topology, shape, impl):
+    """Every conv geometry of the shipped configs, with the fused prologue (upsample + unpool) and LeakyReLU epilogue."""
+    lvl, ci, co, k, s, t_in, up, unpool_lvl = shape
+    ops.set_conv_impl(ops.IMPL_SIMT if impl == "simt" else ops.IMPL_AUTO)
+    tol = 1e-5 if impl == "simt" else 2e-3
+    topo = golden_topology["levels"]
+    nb = topo[lvl]["neighbours"]
+    j = len(nb)
+    b = 5
+    torch.manual_seed(lvl * 100 + k)
+    conv = H.SkeletonConv(nb, j * ci, j * co, k, j, stride=s, padding=(k - 1) // 2, bias=True, padding_mode="reflection")
+    w, bias, mask = conv.weight.detach().clone(), conv.bias.detach().clone(), conv.mask.detach().clone()
+    conv = conv.to(DEV)
+    if unpool_lvl is not None:
+        pl = topo[unpool_lvl]["pooling_list"]
+        src_j = len(pl)
+        t_src = t_in // 2
+        x = torch.randn(b, src_j * ci, t_src)
+        un = H.SkeletonUnpool(pl, ci)
+        xr = x.clone().requires_grad_(True)
+        ref_in = O.skeleton_unpool(O.upsample2_linear(xr), pl, ci)
+        xm = x.to(DEV).requires_grad_(True)
+        y = conv.fused_forward(xm, upsample=True, unpool_src=un.src, src_joints=src_j, lrelu=True)
+    else:
+        x = torch.randn(b, j * ci, t_in)
+        xr = x.clone().requires_grad_(True)
+        ref_in = xr
+        xm = x.to(DEV).requires_grad_(True)
+        y = conv.fused_forward(xm, lrelu=True)
+    wr, br = w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    ref = torch.nn.functional.leaky_relu(O.skeleton_conv(ref_in, wr, mask, br, s, (k - 1) // 2, "reflection"), 0.2)
+    gy = torch.randn_like(ref)
+    ref.backward(gy)
+    y.backward(gy.to(DEV))
+    assert y.shape == ref.shape
+    assert rel_l2(y.detach().cpu(), ref.detach()) < tol
+    assert rel_l2(xm.grad.cpu(), xr.grad) < tol
+    assert rel_l2(conv.weight.grad.cpu(), wr.grad) < tol
+    assert rel_l2(conv.bias.grad.cpu(), br.grad) < tol
+    ops.set_conv_impl(ops.IMPL_AUTO)
+
+
+def test_conv_reflect_pad_too_large_is_an_error(golden_topology):
+    nb = golden_topology["levels"][3]["neighbours"]
+    conv = H.SkeletonConv(nb, 7 * 2, 7 * 2, 15, 7, padding=7, padding_mode="reflection").to(DEV)
+    with pytest.raises(Exception, match="reflect"):
+        conv(torch.zeros(1, 14, 7, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------ fused losses, Adam
+def test_latent_vs_oracle():
+    gen = torch.Generator().manual_seed(11)
+    dist = torch.randn(70, 48, generator=gen)
+    eps = torch.randn(70, 24, generator=gen)
+    dr = dist.clone().requires_grad_(True)
+    mu, lv = dr[:, :24], dr[:, 24:]
+    z_ref = eps * torch.exp(0.5 * lv) + mu
+    kl_ref = O.kl_loss(lv, mu)
+    gz = torch.randn(70, 24, generator=gen)
+    (z_ref * gz).sum().backward(retain_graph=True)
+    (0.003 * kl_ref).backward()
+    dm = dist.to(DEV).requires_grad_(True)
+    z, kl = ops.latent_sample_kl(dm, eps.to(DEV), 24)
+    torch.autograd.backward([z, kl], [gz.to(DEV), torch.tensor(0.003 / 70, device=DEV)])
+    assert rel_l2(z.detach().cpu(), z_ref.detach()) < 1e-6
+    assert abs(float(kl) / 70 - float(kl_ref)) < 1e-5 * abs(float(kl_ref))
+    assert rel_l2(dm.grad.cpu(), dr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("b,t", [(2, 64), (3, 8), (7, 33)])
+def test_recon_fused_vs_oracle(smpl, b, t):
+    gen = torch.Generator().manual_seed(b * 100 + t)
+    parents, off = smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])
+    batch = O.synthetic_batch(b, t, parents, off, seed=77)
+    pred = torch.randn(b, 144, t, generator=gen)                     # decoder output, NCW
+    pr = pred.clone().requires_grad_(True)
+    x6 = pr.transpose(1, 2).contiguous().view(b * t, 24, 6)
+    rot = O.rot6d_to_rotmat(x6)
+    pos = O.forward_kinematics(rot, parents, off)
+    gt_pos = O.forward_kinematics(batch["seq_rot_mat"].view(b * t, 24, 3, 3), parents, off)
+    l6 = O.l2_criterion(x6.view(b, t, -1), batch["seq_rot_6d"])
+    lr = O.l2_criterion(rot.view(b, t, -1), batch["seq_rot_mat"])
+    lp = O.l2_criterion(pos.view(b, t, -1), gt_pos.view(b, t, -1))
+    (1.0 * l6 + 1.0 * lr + 10.0 * lp).backward()
+    for ncw in (True, False):
+        sums = torch.zeros(4, device=DEV)
+        inp = pred.to(DEV) if ncw else pred.transpose(1, 2).contiguous().to(DEV)
+        dx = ops.recon_fwdbwd(inp, ncw, batch["seq_rot_6d"].to(DEV), batch["seq_rot_mat"].to(DEV), off.to(DEV), parents,
+                              1.0, 1.0, 10.0, sums)
+        nf = b * t
+        got = [float(sums[0]) / (nf * 144), float(sums[1]) / (nf * 216), float(sums[2]) / (nf * 72)]
+        np.testing.assert_allclose(got, [float(l6), float(lr), float(lp)], rtol=1e-5)
+        ref_g = pr.grad if ncw else pr.grad.transpose(1, 2)
+        assert rel_l2(dx.cpu(), ref_g) < 1e-5
+
+
+def test_fused_adam_vs_torch():
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(288, 144, 15), (288,), (24, 384), (7,)]
+    ps = [torch.randn(*s, generator=gen) for s in shapes]
+    ref_p = [p.clone().requires_grad_(True) for p in ps]
+    opt_ref = torch.optim.Adam(ref_p, lr=1e-4, weight_decay=1e-4)
+    mine_p = [p.clone().to(DEV).requires_grad_(True) for p in ps]
+    opt = ops.FusedAdam(mine_p, lr=1e-4, weight_decay=1e-4)
+    for step in range(5):
+        gs = [torch.randn(*s, generator=gen) for s in shapes]
+        for p, g in zip(ref_p, gs):
+            p.grad = g.clone()
+        for p, g in zip(mine_p, gs):
+            p.grad = g.clone().to(DEV)
+        opt_ref.step()
+        opt.step()
+    for a, b in zip(mine_p, ref_p):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ whole-model steps
+def _load(model, oracle):
+    sd = model.state_dict()
+    for k, v in oracle.params.items():
+        assert k in sd, k
+        sd[k] = v.detach().clone()
+    model.load_state_dict(sd)
+    return model.to(DEV)
+
+
+@pytest.mark.parametrize("tag,hp,bs", [("len64", HP64, 2), ("len8", HP8, 3)])
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_hmvae_step_vs_reference_golden(tag, hp, bs, impl, golden_models, smpl):
+    """Same seeded weights / inputs / epsilon as the golden run of the REAL reference forward+backward."""
+    g = golden_models
+    ops.set_conv_impl(ops.IMPL_SIMT if impl == "simt" else ops.IMPL_AUTO)
+    tol_l, tol_g = (2e-5, 2e-3) if impl == "simt" else (2e-3, 5e-3)
+    parents, off = smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])
+    ora = O.HMVAEOracle(hp, parents, off).init(seed=0)
+    model = _load(TwoHierSAVAEModel(dict(hp), device=DEV), ora)
+    batch = O.synthetic_batch(bs, hp["train_seq_len"], parents, off, seed=1234)
+    eps = O.draw_eps(ora, bs, seed=4321)
+    data = (batch["seq_rot_6d"], batch["seq_rot_mat"], None, None, None, None, batch["seq_root_v"])
+    for it_tag, iters in [("it0", 0), ("itlate", hp["iteration_interval"] + 1)]:
+        model.zero_grad(set_to_none=True)
+        res = model(data, hp, iters, eps_list=eps)
+        mine = [float(res[i]) for i in range(5)] + [float(res[9][0]), float(res[9][3])]
+        np.testing.assert_allclose(mine, g[f"{tag}_{it_tag}_losses"], rtol=tol_l)
+        for k, p in model.named_parameters():
+            if k.startswith("dec.enc.") or not p.requires_grad:
+                continue
+            refc = g[f"{tag}_{it_tag}_grad/{k}"]
+            if np.isnan(refc).all():
+                assert p.grad is None or float(p.grad.abs().sum()) == 0.0, k
+            else:
+                np.testing.assert_allclose(_cks(p.grad.cpu()), refc, rtol=tol_g, atol=1e-6, err_msg=k)
+        if it_tag == "it0":
+            assert rel_l2(model.enc.convs[0].bias.grad.cpu(), g[f"{tag}_gb_enc0"]) < tol_g
+            assert rel_l2(model.dec.convs[3].bias.grad.cpu(), g[f"{tag}_gb_dec3"]) < tol_g
+    sz = [cu(g[f"{tag}_test_z{i}"]) for i in range(4)]
+    hp2 = dict(hp, random_root_rot_flag=False)
+    gt, mean, samp, _ = model.test(data, hp2, 0, sampled_z_list=sz)
+    tol_p = 2e-5 if impl == "simt" else 2e-3
+    np.testing.assert_allclose(gt.cpu().numpy(), g[f"{tag}_test_gt"], atol=1e-5)
+    np.testing.assert_allclose(mean.cpu().numpy(), g[f"{tag}_test_mean"], atol=tol_p)
+    np.testing.assert_allclose(samp.cpu().numpy(), g[f"{tag}_test_sampled"], atol=tol_p)
+    ops.set_conv_impl(ops.IMPL_AUTO)
+
+
+def test_hmvae_full_batch_vs_oracle(smpl):
+    """BASELINE config 1 size (B=32, len64): losses and gradients against the oracle on the CPU."""
+    parents, off = smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])
+    ora = O.HMVAEOracle(HP64, parents, off).init(seed=0)
+    model = _load(TwoHierSAVAEModel(dict(HP64), device=DEV), ora)
+    batch = O.synthetic_batch(32, 64, parents, off, seed=1234)
+    eps = O.draw_eps(ora, 32, seed=4321)
+    ref = ora.step(batch["seq_rot_6d"], batch["seq_rot_mat"], eps, iterations=0)
+    res = model((batch["seq_rot_6d"], batch["seq_rot_mat"]), HP64, 0, eps_list=eps)
+    np.testing.assert_allclose(float(res[0]), float(ref["total"]), rtol=2e-3)
+    np.testing.assert_allclose(float(res[4]), float(ref["rec_pose"]), rtol=2e-3)
+    for k, p in model.named_parameters():
+        if k.startswith("dec.enc.") or not p.requires_grad or ora.params[k].grad is None:
+            continue
+        assert rel_l2(p.grad.cpu(), ora.params[k].grad) < 5e-3, k
+
+
+def test_trajectory_step_vs_reference_golden(golden_models, smpl):
+    g = golden_models
+    parents, off = smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])
+    ms = torch.from_numpy(smpl["mean_std"])
+    ora = O.TrajectoryOracle(HPT, ms, parents).init(seed=0)
+    model = _load(TrajectoryModel(dict(HPT), device=DEV), ora)
+    batch = O.synthetic_batch(2, 128, parents, off, seed=1234, mean_std=ms)
+    data = (batch["seq_rot_6d"], batch["seq_rot_mat"], batch["seq_rot_pos"], batch["seq_joint_pos"], None, None, batch["seq_root_v"])
+    res = model(data, HPT, 0)
+    np.testing.assert_allclose([float(res[0]), float(res[6]), float(res[8])], g["traj_losses"], rtol=2e-3)
+    for k, p in model.named_parameters():
+        if p.requires_grad:
+            np.testing.assert_allclose(_cks(p.grad.cpu()), g[f"traj_grad/{k}"], rtol=5e-3, atol=1e-6, err_msg=k)
+    assert rel_l2(model.fc_mapping.bias.grad.cpu(), g["traj_gb_fc"]) < 2e-3
