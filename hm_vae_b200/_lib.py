@@ -17,15 +17,19 @@ class HmvaeError(RuntimeError):
     pass
 
 
+def _build_library():
+    if os.environ.get("HMVAE_AUTOBUILD", "1") != "1":
+        raise HmvaeError("libhmvae_b200.so is missing or stale: run `python -m hm_vae_b200.build` (nvcc, sm_100a)")
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_hmvae_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+
+
 if not os.path.exists(LIB_PATH):
-    if os.environ.get("HMVAE_AUTOBUILD", "1") == "1":
-        from . import build as _build
-
-        _build.build()
-    else:
-        raise HmvaeError("libhmvae_b200.so is missing: run `python -m hm_vae_b200.build` (nvcc, sm_100a)")
-
-lib = ctypes.CDLL(LIB_PATH)
+    _build_library()
 
 
 class ConvDesc(Structure):
@@ -70,12 +74,25 @@ _SIGS = {
     "hmvae_mse_bwd": (c_int, [P, P, P, c_long, c_float, P]),
     "hmvae_traj_fwdbwd": (c_int, [P, P, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, c_float, c_float, P, P, P]),
     "hmvae_adam_step": (c_int, [POINTER(AdamTensor), c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
+    "hmvae_adam_step_dyn": (c_int, [POINTER(AdamTensor), c_int, P, c_float, c_float, c_float, c_float, c_float, P]),
 }
 EXPORTS = sorted(_SIGS)
-for _name, (_res, _args) in _SIGS.items():
-    _fn = getattr(lib, _name)     # AttributeError here == the header and the library disagree
-    _fn.restype = _res
-    _fn.argtypes = _args
+
+
+def _bind():
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(handle, name)     # AttributeError here == the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    return handle
+
+
+try:
+    lib = _bind()
+except AttributeError:                  # stale library from an older source tree: rebuild once, then fail loudly
+    _build_library()
+    lib = _bind()
 
 
 def check(rc, what=""):

@@ -258,7 +258,12 @@ struct AdamPack {
 };
 
 __global__ void __launch_bounds__(EW_TPB) adam_kernel(AdamPack pack, float lr_over_bc1, float inv_sqrt_bc2, float beta1,
-                                                      float beta2, float eps, float wd, float gscale) {
+                                                      float beta2, float eps, float wd, float gscale,
+                                                      const float* __restrict__ dyn2) {
+  if (dyn2) {
+    lr_over_bc1 = dyn2[0];
+    inv_sqrt_bc2 = dyn2[1];
+  }
   const hmvae_adam_tensor T = pack.t[blockIdx.y];
   float* __restrict__ p = T.p;
   const float* __restrict__ g = T.g;
@@ -446,13 +451,9 @@ extern "C" int hmvae_traj_fwdbwd(const float* root_v_pred, const float* root_v_g
   return check_launch("traj_fwdbwd");
 }
 
-extern "C" int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2,
-                               float eps, float weight_decay, int step, float grad_scale, void* stream) {
-  if (!tensors || n_tensors < 0 || step < 1) return fail_arg("adam_step: bad arguments");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float lr_over_bc1 = (float)((double)lr / bc1);
-  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+static int adam_launch(const hmvae_adam_tensor* tensors, int n_tensors, float lr_over_bc1, float inv_sqrt_bc2,
+                       const float* dyn2, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                       void* stream) {
   for (int base = 0; base < n_tensors; base += ADAM_MAX_T) {
     AdamPack pack;
     const int cnt = n_tensors - base < ADAM_MAX_T ? n_tensors - base : ADAM_MAX_T;
@@ -469,9 +470,24 @@ extern "C" int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, 
     if (bx > cap) bx = cap;
     dim3 grid((unsigned)bx, (unsigned)cnt);
     adam_kernel<<<grid, EW_TPB, 0, (cudaStream_t)stream>>>(pack, lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, weight_decay,
-                                                          grad_scale);
+                                                          grad_scale, dyn2);
     int rc = check_launch("adam_step");
     if (rc) return rc;
   }
   return 0;
+}
+
+extern "C" int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2,
+                               float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  if (!tensors || n_tensors < 0 || step < 1) return fail_arg("adam_step: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  return adam_launch(tensors, n_tensors, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), nullptr, beta1, beta2, eps,
+                     weight_decay, grad_scale, stream);
+}
+
+extern "C" int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const float* dyn2, float beta1,
+                                   float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+  if (!tensors || n_tensors < 0 || !dyn2) return fail_arg("adam_step_dyn: bad arguments");
+  return adam_launch(tensors, n_tensors, 0.f, 0.f, dyn2, beta1, beta2, eps, weight_decay, grad_scale, stream);
 }

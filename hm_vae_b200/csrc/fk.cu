@@ -493,6 +493,7 @@ using namespace hmvae;
 
 extern "C" int hmvae_fk_fwd(const float* rot, int rot_dim, const float* offsets, const float* positions,
                             const int* parents, int joints, long n, float* pos, float* rotmat_out, void* stream) {
+  if (n <= 0) return 0;
   if (!rot || !pos || !parents || (!offsets && !positions)) return fail_arg("fk_fwd: null pointer");
   if (rot_dim != 9 && rot_dim != 6) return fail_arg("fk_fwd: rot_dim must be 9 (3x3) or 6");
   if (rotmat_out && rot_dim != 6) return fail_arg("fk_fwd: rotmat_out only with 6D input");
@@ -520,6 +521,7 @@ extern "C" int hmvae_fk_fwd(const float* rot, int rot_dim, const float* offsets,
 extern "C" int hmvae_fk_bwd(const float* rot, int rot_dim, const float* offsets, const float* positions,
                             const int* parents, int joints, long n, const float* dpos, const float* drotmat_extra,
                             float* drot, void* stream) {
+  if (n <= 0) return 0;
   if (!rot || !dpos || !drot || !parents || (!offsets && !positions)) return fail_arg("fk_bwd: null pointer");
   if (rot_dim != 9 && rot_dim != 6) return fail_arg("fk_bwd: rot_dim must be 9 (3x3) or 6");
   if (drotmat_extra) return fail_arg("fk_bwd: drotmat_extra is not supported (add it to drot on the caller side)");
@@ -543,6 +545,7 @@ extern "C" int hmvae_fk_bwd(const float* rot, int rot_dim, const float* offsets,
 }
 
 extern "C" int hmvae_rot6d_fwd(const float* x6, float* rotmat, long m, void* stream) {
+  if (m <= 0) return 0;
   if (!x6 || !rotmat) return fail_arg("rot6d_fwd: null pointer");
   if (!aligned16(x6) || !aligned16(rotmat)) return fail_arg("rot6d_fwd: pointers must be 16-byte aligned");
   if (m <= 0) return 0;
@@ -553,6 +556,7 @@ extern "C" int hmvae_rot6d_fwd(const float* x6, float* rotmat, long m, void* str
 }
 
 extern "C" int hmvae_rot6d_bwd(const float* x6, const float* drotmat, float* dx6, long m, void* stream) {
+  if (m <= 0) return 0;
   if (!x6 || !drotmat || !dx6) return fail_arg("rot6d_bwd: null pointer");
   if (!aligned16(x6) || !aligned16(drotmat) || !aligned16(dx6)) return fail_arg("rot6d_bwd: pointers must be 16-byte aligned");
   if (m <= 0) return 0;
@@ -563,6 +567,7 @@ extern "C" int hmvae_rot6d_bwd(const float* x6, const float* drotmat, float* dx6
 }
 
 extern "C" int hmvae_aa2rot_fwd(const float* aa, float* out44, long m, void* stream) {
+  if (m <= 0) return 0;
   if (!aa || !out44) return fail_arg("aa2rot_fwd: null pointer");
   if (!aligned16(out44)) return fail_arg("aa2rot_fwd: output must be 16-byte aligned");
   if (m <= 0) return 0;

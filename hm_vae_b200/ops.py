@@ -403,15 +403,42 @@ class FusedAdam:
             elif p.grad is not None:
                 p.grad.zero_()
 
-    def step(self, grad_scale=1.0, lr=None, step=None):
-        self.step_count = self.step_count + 1 if step is None else step
+    def _pack(self):
         live = [(p, m, v) for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq) if p.grad is not None]
         arr = (_lib.AdamTensor * len(live))()
         for i, (p, m, v) in enumerate(live):
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
             arr[i] = _lib.AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
-        check(lib.hmvae_adam_step(arr, len(live), self.param_groups[0]["lr"] if lr is None else lr, self.betas[0], self.betas[1],
+        return arr, len(live)
+
+    def step(self, grad_scale=1.0, lr=None, step=None):
+        self.step_count = self.step_count + 1 if step is None else step
+        arr, n = self._pack()
+        check(lib.hmvae_adam_step(arr, n, self.param_groups[0]["lr"] if lr is None else lr, self.betas[0], self.betas[1],
                                   self.eps, self.weight_decay, self.step_count, grad_scale, stream()), "adam_step")
+
+    # ---- CUDA-graph friendly variant: step-dependent scalars travel through a pinned host -> device copy
+    def dyn_buffers(self, device):
+        if not hasattr(self, "_dyn_host"):
+            self._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self._dyn_dev = torch.zeros(2, dtype=torch.float32, device=device)
+        return self._dyn_host, self._dyn_dev
+
+    def advance(self, lr=None):
+        """Host side of one step: bumps t and refreshes {lr/(1-b1^t), 1/sqrt(1-b2^t)} in the pinned buffer."""
+        self.step_count += 1
+        lr = self.param_groups[0]["lr"] if lr is None else lr
+        host, _ = self.dyn_buffers(self.params[0].device)
+        host[0] = lr / (1.0 - self.betas[0] ** self.step_count)
+        host[1] = 1.0 / (1.0 - self.betas[1] ** self.step_count) ** 0.5
+
+    def step_dyn(self, grad_scale=1.0):
+        """Device side (capturable): H2D copy of the two scalars + the multi-tensor kernel.  Call advance() first."""
+        host, dev = self.dyn_buffers(self.params[0].device)
+        dev.copy_(host, non_blocking=True)
+        arr, n = self._pack()
+        check(lib.hmvae_adam_step_dyn(arr, n, ptr(dev), self.betas[0], self.betas[1], self.eps, self.weight_decay, grad_scale,
+                                      stream()), "adam_step_dyn")
 
     def state_dict(self):
         return dict(step=self.step_count, lr=self.param_groups[0]["lr"], exp_avg=[m.clone() for m in self.exp_avg],

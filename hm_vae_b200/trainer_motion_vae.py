@@ -1,0 +1,185 @@
+"""Host mirror of the reference Trainer (trainer_motion_vae.py:15-135, 251-283) around the B200 step.
+
+Same surface: ``Trainer(cfg)``, ``gen_update(data, hp, iterations, multigpus, validation_flag)``, ``save`` /
+``resume`` / ``load_ckpt`` with the reference's file names and dict layout (``gen_%08d.pt`` = {'state_dict': ...},
+``optimizer.pt`` = {'gen': ...}), Adam(lr, weight_decay) + StepLR.  Differences:
+  * the optimiser is the fused multi-tensor kernel (``ops.FusedAdam``), LR schedule evaluated on the host;
+  * the 9 ``.item()`` host syncs per step of the reference (:95-98) are opt-in (``sync_losses``);
+  * ``enable_cuda_graph`` captures forward+backward+all-reduce+Adam once and replays it each step;
+  * multi-GPU is one process per GPU with bucketed NCCL all-reduce (``ddp.BucketedAllReduce``), not DataParallel.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.init as init
+
+from . import ops
+from .ddp import BucketedAllReduce
+from .seq_two_hier_sa_vae import TwoHierSAVAEModel
+from .trajectory_pred_model import TrajectoryModel
+
+
+def weights_init(init_type='gaussian'):
+    """trainer_motion_vae.py:264-283 -- only modules whose class name STARTS with 'Conv' or 'Linear' are touched,
+    i.e. nn.Linear but not SkeletonConv."""
+
+    def init_fun(m):
+        classname = m.__class__.__name__
+        if (classname.find('Conv') == 0 or classname.find('Linear') == 0) and hasattr(m, 'weight'):
+            if init_type == 'gaussian':
+                init.normal_(m.weight.data, 0.0, 0.02)
+            elif init_type == 'xavier':
+                init.xavier_normal_(m.weight.data, gain=math.sqrt(2))
+            elif init_type == 'kaiming':
+                init.kaiming_normal_(m.weight.data, a=0, mode='fan_in')
+            elif init_type == 'orthogonal':
+                init.orthogonal_(m.weight.data, gain=math.sqrt(2))
+            elif init_type == 'default':
+                pass
+            else:
+                assert 0, "Unsupported initialization: {}".format(init_type)
+            if hasattr(m, 'bias') and m.bias is not None:
+                init.constant_(m.bias.data, 0.0)
+
+    return init_fun
+
+
+def get_model_list(dirname, key):
+    if not os.path.exists(dirname):
+        return None
+    models = sorted(os.path.join(dirname, f) for f in os.listdir(dirname)
+                    if os.path.isfile(os.path.join(dirname, f)) and key in f and ".pt" in f)
+    return models[-1] if models else None
+
+
+class Trainer(nn.Module):
+    def __init__(self, cfg, device=None, sync_losses=True, n_buckets=4):
+        super(Trainer, self).__init__()
+        if cfg['model_name'] == "TrajectoryModel":
+            self.model = TrajectoryModel(cfg, device=device)
+        elif cfg['model_name'] == "TwoHierSAVAEModel":
+            self.model = TwoHierSAVAEModel(cfg, device=device)
+        else:
+            raise ValueError("unknown model_name %r" % cfg['model_name'])
+        self.cfg = cfg
+        self.sync_losses = sync_losses
+        self.apply(weights_init(cfg['init']))
+        self.base_lr = cfg['lr']
+        self.gen_opt = None
+        self._n_buckets = n_buckets
+        self._sync = None
+        self._graphs = {}
+        self._static = None
+
+    # ------------------------------------------------------------------ optimiser / schedule
+    def _ensure_opt(self):
+        if self.gen_opt is None:
+            params = [p for p in self.model.parameters() if p.requires_grad]
+            self.gen_opt = ops.FusedAdam(params, lr=self.base_lr, weight_decay=self.cfg['weight_decay'])
+            self._sync = BucketedAllReduce(self.model, n_buckets=self._n_buckets)
+
+    def lr_at(self, iterations):
+        """StepLR(step_size, gamma) (trainer_motion_vae.py:251-262); 'constant' when no policy is configured."""
+        if self.cfg.get('lr_policy', 'constant') == 'step':
+            return self.base_lr * self.cfg['gamma'] ** (iterations // self.cfg['step_size'])
+        return self.base_lr
+
+    # ------------------------------------------------------------------ one step
+    def _device_step(self, data, hp, iterations):
+        self.gen_opt.zero_grad(set_to_none=True)
+        self._sync.begin()
+        out = self.model(data, hp, iterations)
+        self._sync.finish()
+        self.gen_opt.step_dyn(grad_scale=1.0 / self._sync.world)
+        return out
+
+    def _record(self, out, validation):
+        names = ["total", "kl", "rec_6d", "rec_rot", "rec_pose", "rec_joint_pos", "rec_root_v", "rec_linear_v", "rec_angular_v"]
+        prefix = "loss_val_" if validation else "loss_"
+        for n, v in zip(names, out[:9]):
+            setattr(self, prefix + n, torch.mean(v))
+        if len(out) > 9:
+            for i, v in enumerate(out[9]):
+                setattr(self, "loss_hier_kl_%d" % (i + 1), torch.mean(v))
+        if not self.sync_losses:
+            return tuple(torch.mean(v) for v in out[:9])
+        vals = torch.stack([torch.mean(v).reshape(()) for v in out[:9]]).tolist()      # ONE device->host sync
+        return tuple(vals)
+
+    def gen_update(self, data, hp, iterations, multigpus=False, validation_flag=False):
+        self._ensure_opt()
+        if validation_flag:
+            with torch.no_grad():
+                out = self.model(data, hp, iterations, validation_flag=True)
+            return self._record(out, True)
+        key = self._graph_key(hp, iterations, data)
+        self.gen_opt.advance(lr=self.lr_at(iterations))
+        if key in self._graphs:
+            graph, static_in, static_out = self._graphs[key]
+            for dst, src in zip(static_in, data):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            graph.replay()
+            out = static_out
+        else:
+            out = self._device_step(data, hp, iterations)
+        return self._record(out, False)
+
+    # ------------------------------------------------------------------ CUDA graph of the whole step
+    def _graph_key(self, hp, iterations, data):
+        detach = iterations < hp.get('iteration_interval', 0)
+        shapes = tuple(tuple(d.shape) if torch.is_tensor(d) else None for d in data)
+        return (detach, shapes)
+
+    def enable_cuda_graph(self, data, hp, iterations, warmup=3):
+        """Captures fwd + bwd (+ all-reduce) + Adam for this batch shape / detach phase.  Inputs are copied into static
+        device buffers before each replay; the LR and Adam's bias corrections reach the graph through a pinned-host
+        -> device copy node (``FusedAdam.step_dyn``).  The warm-up steps are real optimisation steps."""
+        self._ensure_opt()
+        dev = next(self.model.parameters()).device
+        static_in = [d.to(device=dev, dtype=torch.float32).clone() if torch.is_tensor(d) else None for d in data]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.gen_opt.advance(lr=self.lr_at(iterations))
+                self._device_step(static_in, hp, iterations)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.gen_opt.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops._lib.launch_count()
+        with torch.cuda.graph(graph):
+            static_out = self._device_step(static_in, hp, iterations)
+        self.launches_per_step = ops._lib.launch_count() - n0
+        self._graphs[self._graph_key(hp, iterations, data)] = (graph, static_in, static_out)
+        return graph
+
+    # ------------------------------------------------------------------ checkpoints (reference layout)
+    def save(self, snapshot_dir, iterations, multigpus=False):
+        self._ensure_opt()
+        gen_name = os.path.join(snapshot_dir, 'gen_%08d.pt' % (iterations + 1))
+        opt_name = os.path.join(snapshot_dir, 'optimizer.pt')
+        torch.save({'state_dict': self.model.state_dict()}, gen_name, _use_new_zipfile_serialization=False)
+        torch.save({'gen': self.gen_opt.state_dict()}, opt_name, _use_new_zipfile_serialization=False)
+
+    def resume(self, checkpoint_dir, hp, multigpus=False):
+        self._ensure_opt()
+        last_model_name = get_model_list(checkpoint_dir, "gen")
+        self.load_ckpt(last_model_name)
+        iterations = int(last_model_name[-11:-3])
+        state = torch.load(os.path.join(checkpoint_dir, 'optimizer.pt'), weights_only=False)
+        self.gen_opt.load_state_dict(state['gen'])
+        print('Resume from iteration %d' % iterations)
+        return iterations
+
+    def load_ckpt(self, ckpt_name):
+        state_dict = torch.load(ckpt_name, weights_only=False)
+        model_dict = self.model.state_dict()
+        model_dict.update(state_dict['state_dict'])
+        self.model.load_state_dict(model_dict)
+
+    def test(self, data, hp, iterations):
+        return self.model.test(data, hp, iterations)

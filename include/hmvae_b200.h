@@ -163,6 +163,10 @@ typedef struct {
 } hmvae_adam_tensor;
 int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, float grad_scale, void* stream);
+/* Same, but the two step-dependent scalars {lr/(1-b1^t), 1/sqrt(1-b2^t)} are read from DEVICE memory (float[2]) so that
+ * a CUDA graph of the whole training step can be replayed while the host advances t and the LR schedule. */
+int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const float* dyn2, float beta1, float beta2,
+                        float eps, float weight_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }
