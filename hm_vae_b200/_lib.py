@@ -28,7 +28,21 @@ def _build_library():
     mod.build()
 
 
-if not os.path.exists(LIB_PATH):
+def _stale():
+    """Library older than a kernel source / header (dlopen caches by path, so this is decided BEFORE loading)."""
+    if not os.path.exists(LIB_PATH):
+        return True
+    import shutil
+
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        return False
+    t = os.path.getmtime(LIB_PATH)
+    csrc = os.path.join(_HERE, "csrc")
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(os.path.dirname(_HERE), "include", "hmvae_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+if _stale():
     _build_library()
 
 
@@ -53,6 +67,11 @@ _SIGS = {
     "hmvae_conv_dgrad": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_conv_wgrad": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "hmvae_conv_prologue_bwd": (c_int, [P, P, P, P, c_int, c_int, P]),
+    "hmvae_conv_tc_supported": (c_int, [P, c_int, c_int, c_int]),
+    "hmvae_conv_packed_size": (c_int, [P, POINTER(c_long), POINTER(c_long)]),
+    "hmvae_conv_pack_weights": (c_int, [P, P, P, P, P]),
+    "hmvae_conv_fprop_tc": (c_int, [P, P, P, P, P, c_int, c_int, P]),
+    "hmvae_conv_dgrad_tc": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "hmvae_pool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, IP, IP, c_int, P]),
     "hmvae_pool_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, IP, IP, c_int, P]),
     "hmvae_unpool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, IP, P]),

@@ -19,9 +19,11 @@ int num_sms() {
   return cached;
 }
 
-int conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float* w, const float* bias, float* y, int B, int T,
-                  cudaStream_t st);
-bool conv_fprop_tc_supported(const hmvae_conv_plan* plan, int B, int T);
+bool conv_tc_supported(const hmvae_conv_plan* plan, int B, int T, int mode);
+void conv_packed_sizes(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad);
+int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* wp_d, cudaStream_t st);
+int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, const float* wp,
+                   const float* bias, float* dst, int B, int T, cudaStream_t st);
 }  // namespace hmvae
 
 using namespace hmvae;
@@ -117,12 +119,44 @@ extern "C" int hmvae_conv_fprop(const hmvae_conv_plan* plan, const float* x, con
   if (rc) return rc;
   if (!x || !w || !y) return fail_arg("conv_fprop: null pointer");
   if (batch == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 2 || (impl == 0 && conv_fprop_tc_supported(plan, batch, t_in))) {
-    if (!conv_fprop_tc_supported(plan, batch, t_in)) return fail_arg("conv_fprop: tcgen05 path does not support this shape");
-    return conv_fprop_tc(plan, x, w, bias, y, batch, t_in, st);
-  }
-  return conv_fprop_simt(plan, x, w, bias, y, batch, t_in, st);
+  (void)impl;
+  return conv_fprop_simt(plan, x, w, bias, y, batch, t_in, (cudaStream_t)stream);
+}
+
+extern "C" int hmvae_conv_tc_supported(const hmvae_conv_plan* plan, int batch, int t_in, int mode) {
+  if (!plan || batch < 1 || t_in < 1 || (mode != 0 && mode != 1)) return 0;
+  if (check_shape(plan, batch, t_in, "conv_tc_supported")) return 0;
+  return conv_tc_supported(plan, batch, t_in, mode) ? 1 : 0;
+}
+
+extern "C" int hmvae_conv_packed_size(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad) {
+  if (!plan || !n_fprop || !n_dgrad) return fail_arg("conv_packed_size: null pointer");
+  conv_packed_sizes(plan, n_fprop, n_dgrad);
+  return 0;
+}
+
+extern "C" int hmvae_conv_pack_weights(const hmvae_conv_plan* plan, const float* w, float* wp_fprop, float* wp_dgrad,
+                                       void* stream) {
+  if (!plan || !w) return fail_arg("conv_pack_weights: null pointer");
+  return conv_pack(plan, w, wp_fprop, wp_dgrad, (cudaStream_t)stream);
+}
+
+extern "C" int hmvae_conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float* wp_fprop, const float* bias,
+                                   float* y, int batch, int t_in, void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_fprop_tc");
+  if (rc) return rc;
+  if (!x || !wp_fprop || !y) return fail_arg("conv_fprop_tc: null pointer");
+  if (batch == 0) return 0;
+  return conv_tc_launch(plan, 0, x, nullptr, wp_fprop, bias, y, batch, t_in, (cudaStream_t)stream);
+}
+
+extern "C" int hmvae_conv_dgrad_tc(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* wp_dgrad,
+                                   float* dxin, int batch, int t_in, void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_dgrad_tc");
+  if (rc) return rc;
+  if (!dy || !wp_dgrad || !dxin || (plan->d.lrelu && !y)) return fail_arg("conv_dgrad_tc: null pointer");
+  if (batch == 0) return 0;
+  return conv_tc_launch(plan, 1, dy, y, wp_dgrad, nullptr, dxin, batch, t_in, (cudaStream_t)stream);
 }
 
 extern "C" int hmvae_conv_dgrad(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* w, float* dxin,

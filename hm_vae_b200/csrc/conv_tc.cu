@@ -1,8 +1,475 @@
-// tcgen05 (TF32, TMEM accumulators) implementation of the skeleton-aware conv -- placeholder until bring-up.
+// Skeleton-aware conv on the 5th-gen tensor cores: tcgen05.mma kind::tf32, FP32 accumulators in TMEM.   sm_100a only.
+//
+// "Shift-GEMM" formulation (conv).  For one output joint j and one input joint n in its neighbour list
+//     D_j[m, o] += sum_k  A_n[m + shift(k), c] * W_{j,n,k}[o, c]
+// where the rows of A are (time, sequence) pairs laid out time-major/sequence-minor in shared memory, 16 bytes
+// (4 tf32 channels) per row and per K-chunk.  In the canonical no-swizzle K-major UMMA layout (8-row core matrices
+// packed back to back, SBO = 128 B, LBO = chunk stride) the operand for tap k is the SAME tile with its start address
+// advanced by shift(k) rows, so no im2col expansion is ever materialised: one staged activation tile feeds all K taps
+// and every output joint that has n as a neighbour.  Masked (j, n) blocks are never visited.
+//   * fprop : rows = (t_out, b); stride-2 layers keep even/odd input phases in two row ranges so taps stay shifts.
+//   * dgrad : same kernel with the roles of the channel sets swapped, transposed neighbour lists, flipped taps and a
+//             zero-inserting loader (stride 2); the reflect-padding adjoint is folded in the epilogue.
+// Weights come from a packed, tf32-rounded copy ([block][tap][c/4][n_pad][4]) refreshed by hmvae_conv_pack_weights
+// whenever the dense parameter changes, and are moved with 1-D bulk (TMA) copies.
+//
+// Warp roles (192 threads): warp 0 = weight producer (cp.async.bulk + mbarrier expect_tx), warp 1 = TMEM allocator and
+// single-thread MMA issuer, warps 2-5 = activation producers (global -> tf32 -> smem, with the fused pad / upsample /
+// unpool / lrelu' index math), then the epilogue (tcgen05.ld -> smem transpose -> coalesced store with bias / LeakyReLU /
+// reflect fold).  smem stages cycle through full/empty mbarriers; tcgen05.commit releases a stage.
 #include "conv_common.cuh"
+
 namespace hmvae {
-bool conv_fprop_tc_supported(const hmvae_conv_plan*, int, int) { return false; }
-int conv_fprop_tc(const hmvae_conv_plan*, const float*, const float*, const float*, float*, int, int, cudaStream_t) {
-  return fail_arg("conv_fprop: tcgen05 path not built");
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_GJ = 32;
+constexpr int TC_MAX_NB = 16;
+
+struct TcArgs {
+  ConvArgs a;
+  int mode;            // 0 fprop, 1 dgrad
+  const int* off;      // CSR over the N-side joints (fprop: nb_off, dgrad: nbT_off)
+  const int* idx;
+  int n_real, n_pad;   // N-side channels per joint (real, padded to 16)
+  int ck, ck_pad;      // reduction channels per K-side joint (real, padded to 8)
+  int Bt, Tt;          // sequences per tile, rows-per-sequence (M = Tt*Bt <= 128)
+  int rows_alloc;      // smem rows per 16-byte chunk column
+  int Tp2;             // fprop stride 2: rows per phase / Bt
+  int GJ, nbmax, stages;
+  int B, T, T_out;
+  int a_bytes, stage_bytes;
+  int tmem_cols;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
 }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// no-swizzle canonical layout descriptor: start address, LBO (K-chunk stride), SBO (8-row group stride); version 1
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ long tc_out_index(const ConvArgs& a, long b, int j, int o, int t, int T_out) {
+  const int ch = j * a.ojs + a.oco + o;
+  const long ctot = (long)a.J * a.ojs;
+  return a.cl ? (b * T_out + t) * ctot + ch : (b * ctot + ch) * T_out + t;
+}
+
+// ---------------------------------------------------------------------------------------------- weight packing
+// wp[block][k][q][n_pad][4]:  fprop: block = CSR position (j, n), rows = out channels o, cols = in channels c.
+//                             dgrad: block = transposed-CSR position (n, j), rows = in channels c, cols = out channels o.
+__global__ void conv_pack_kernel(ConvArgs a, const float* __restrict__ w, float* __restrict__ wp, int mode, int n_pad,
+                                 int ck_pad, long total) {
+  const int Cin = a.J * a.ci;
+  const int per_blk = a.K * ck_pad * n_pad;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int blk = (int)(e / per_blk);
+    int r = (int)(e % per_blk);
+    const int c4 = r & 3; r >>= 2;
+    const int row = r % n_pad; r /= n_pad;
+    const int q = r % (ck_pad / 4);
+    const int k = r / (ck_pad / 4);
+    const int col = q * 4 + c4;
+    float v = 0.f;
+    if (mode == 0) {
+      const int j = a.blk_j[blk], n = a.blk_n[blk];
+      if (row < a.co && col < a.ci) v = w[((long)(j * a.co + row) * Cin + n * a.ci + col) * a.K + k];
+    } else {
+      // transposed CSR: find (n, j) of this block
+      int n = 0;
+      while (a.nbT_off[n + 1] <= blk) ++n;
+      const int j = a.nbT_idx[blk];
+      if (row < a.ci && col < a.co) v = w[((long)(j * a.co + col) * Cin + n * a.ci + row) * a.K + k];
+    }
+    wp[e] = __uint_as_float(to_tf32(v));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+struct TcWork {
+  int cnt[64];
+  unsigned char jl[64][TC_MAX_NB];
+  int blk[64][TC_MAX_NB];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const float* __restrict__ src,
+                                                                const float* __restrict__ yact,
+                                                                const float* __restrict__ wp,
+                                                                const float* __restrict__ bias, float* __restrict__ dst) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ TcWork work;
+
+  const ConvArgs& a = p.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y;
+  const int j0 = g * p.GJ;
+  const int gj = (a.J - j0 < p.GJ) ? a.J - j0 : p.GJ;
+  const int b0 = blockIdx.x * p.Bt;
+  const int ncb = p.ck_pad / 8;
+
+  // ---- setup: barriers, TMEM, per-CTA work table
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1 + 4);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int n = tid; n < a.J; n += TC_THREADS) {
+    int c = 0;
+    for (int jl = 0; jl < gj; ++jl) {
+      const int j = j0 + jl;
+      for (int m = p.off[j]; m < p.off[j + 1]; ++m)
+        if (p.idx[m] == n && c < TC_MAX_NB) {
+          work.jl[n][c] = (unsigned char)jl;
+          work.blk[n][c] = m;
+          ++c;
+        }
+    }
+    work.cnt[n] = c;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int rows_alloc = p.rows_alloc;
+  const int blk_floats = a.K * p.ck_pad * p.n_pad;
+
+  if (warp == 0) {
+    // =============================== weight producer (bulk copies) ===============================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int n = 0; n < a.J; ++n) {
+      const int cnt = work.cnt[n];
+      if (cnt == 0) continue;
+      for (int cb = 0; cb < ncb; ++cb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* bsm = smem_raw + (size_t)s * p.stage_bytes + p.a_bytes;
+        const uint32_t piece = (uint32_t)p.n_pad * 32;       // 2 chunks x n_pad rows x 16 B
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)cnt * a.K * piece);
+        __syncwarp();
+        for (int e = lane; e < cnt * a.K; e += 32) {
+          const int slot = e / a.K, k = e % a.K;
+          const float* gsrc = wp + (size_t)work.blk[n][slot] * blk_floats + ((size_t)k * (p.ck_pad / 4) + cb * 2) * p.n_pad * 4;
+          bulk_g2s(bsm + (size_t)(slot * a.K + k) * piece, gsrc, piece, &full_bar[s]);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+    int s = 0;
+    uint32_t ph = 0, started = 0;
+    for (int n = 0; n < a.J; ++n) {
+      const int cnt = work.cnt[n];
+      if (cnt == 0) continue;
+      for (int cb = 0; cb < ncb; ++cb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_u32(smem_raw + (size_t)s * p.stage_bytes);
+          const uint32_t b_base = a_base + p.a_bytes;
+          const uint32_t piece = (uint32_t)p.n_pad * 32;
+          for (int e = 0; e < cnt; ++e) {
+            const int jl = work.jl[n][e];
+            const uint32_t d_addr = tmem_base + (uint32_t)(jl * p.n_pad);
+            for (int k = 0; k < a.K; ++k) {
+              int shift;
+              if (p.mode == 0) shift = (a.s == 1) ? k * p.Bt : ((k & 1) * p.Tp2 + (k >> 1)) * p.Bt;
+              else shift = (a.K - 1 - k) * p.Bt;
+              const uint64_t adesc = tc_desc(a_base + (uint32_t)shift * 16, (uint32_t)rows_alloc * 16, 128);
+              const uint64_t bdesc = tc_desc(b_base + (uint32_t)(e * a.K + k) * piece, (uint32_t)p.n_pad * 16, 128);
+              tc_mma_tf32(d_addr, adesc, bdesc, idesc, (started >> jl) & 1u);
+              started |= 1u << jl;
+            }
+          }
+          tc_commit(&empty_bar[s]);
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+    if (lane == 0) tc_commit(&accum_bar);
+    __syncwarp();
+  } else {
+    // =============================== activation producers (warps 2..5) ===============================
+    const int pt = tid - 64;            // 0..127
+    int s = 0;
+    uint32_t ph = 0;
+    const int Tq = p.T + 2 * a.p;
+    const int tfill = (p.mode == 0) ? Tq : (Tq + a.K - 1);
+    for (int n = 0; n < a.J; ++n) {
+      if (work.cnt[n] == 0) continue;
+      for (int cb = 0; cb < ncb; ++cb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        float4* asm4 = reinterpret_cast<float4*>(smem_raw + (size_t)s * p.stage_bytes);
+        const int items = 2 * p.Bt * tfill;
+        for (int it = pt; it < items; it += 128) {
+          const int r = it % tfill;
+          const int hb = it / tfill;
+          const int b = hb % p.Bt, h = hb / p.Bt;
+          const int c0 = cb * 8 + h * 4;
+          const long bb = b0 + b;
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          int row;
+          if (p.mode == 0) {
+            row = (a.s == 1) ? r * p.Bt + b : ((r & 1) * p.Tp2 + (r >> 1)) * p.Bt + b;
+            if (bb < p.B) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (c0 + i < a.ci) v[i] = load_padded(src, a, bb, n, c0 + i, r, p.T);
+            }
+          } else {
+            row = r * p.Bt + b;
+            const int zz = r - (a.K - 1);
+            if (bb < p.B && zz >= 0 && (zz % a.s) == 0 && zz / a.s < p.T_out) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (c0 + i < a.co) {
+                  const long oi = tc_out_index(a, bb, n, c0 + i, zz / a.s, p.T_out);
+                  float t = src[oi];
+                  if (a.lrelu && !(yact[oi] > 0.f)) t *= 0.2f;
+                  v[i] = t;
+                }
+            }
+          }
+          float4 o;
+          o.x = __uint_as_float(to_tf32(v[0])); o.y = __uint_as_float(to_tf32(v[1]));
+          o.z = __uint_as_float(to_tf32(v[2])); o.w = __uint_as_float(to_tf32(v[3]));
+          asm4[(size_t)h * rows_alloc + row] = o;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+    // =============================== epilogue ===============================
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    float* outs = reinterpret_cast<float*>(smem_raw);          // [gj * n_real][128]   (stage buffers are free now)
+    const int lq = warp & 3;
+    const int m = lq * 32 + lane;
+    for (int jl = 0; jl < gj; ++jl) {
+      for (int c16 = 0; c16 < p.n_pad; c16 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(jl * p.n_pad + c16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c16 + i < p.n_real) outs[(size_t)(jl * p.n_real + c16 + i) * 128 + m] = v[i];
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int nch = gj * p.n_real;
+    if (p.mode == 0) {
+      const int total = nch * p.Bt * p.T_out;
+      for (int e = pt; e < total; e += 128) {
+        const int t = e % p.T_out;
+        const int r = e / p.T_out;
+        const int b = r % p.Bt, ch = r / p.Bt;
+        if (b0 + b < p.B) {
+          const int jl = ch / p.n_real, o = ch % p.n_real;
+          float v = outs[(size_t)ch * 128 + t * p.Bt + b] + (bias ? bias[(j0 + jl) * a.co + o] : 0.f);
+          if (a.lrelu) v = lrelu_f(v, 0.2f);
+          dst[tc_out_index(a, b0 + b, j0 + jl, o, t, p.T_out)] = v;
+        }
+      }
+    } else {
+      const int total = nch * p.Bt * p.T;
+      const int Cin = a.J * a.ci;
+      for (int e = pt; e < total; e += 128) {
+        const int u = e % p.T;
+        const int r = e / p.T;
+        const int b = r % p.Bt, ch = r / p.Bt;
+        if (b0 + b < p.B) {
+          const int jl = ch / p.n_real, c = ch % p.n_real;
+          const float* row = outs + (size_t)ch * 128 + b;
+          float v = row[(u + a.p) * p.Bt];
+          if (a.pad_mode == 1) {
+            if (u >= 1 && u <= a.p) v += row[(a.p - u) * p.Bt];
+            if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += row[(a.p + 2 * (p.T - 1) - u) * p.Bt];
+          }
+          dst[((long)(b0 + b) * Cin + (j0 + jl) * a.ci + c) * p.T + u] = v;
+        }
+      }
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static inline int rup(int v, int m) { return (v + m - 1) / m * m; }
+
+static bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out) {
+  const ConvArgs& a = plan->a;
+  const hmvae_conv_desc& d = plan->d;
+  if (a.J > 64) return false;
+  TcArgs p;
+  p.a = a;
+  p.mode = mode;
+  p.B = B;
+  p.T = T;
+  p.T_out = conv_t_out(d, T);
+  const int Tq = T + 2 * a.p;
+  if (mode == 0) {
+    p.off = a.nb_off; p.idx = a.nb_idx;
+    p.n_real = a.co; p.ck = a.ci;
+    p.Tt = p.T_out;
+  } else {
+    p.off = a.nbT_off; p.idx = a.nbT_idx;
+    p.n_real = a.ci; p.ck = a.co;
+    p.Tt = Tq;
+  }
+  p.n_pad = rup(p.n_real, 16);
+  p.ck_pad = rup(p.ck, 8);
+  if (p.Tt > 128 || p.Tt < 1 || p.n_pad > 256) return false;
+  p.Bt = 128 / p.Tt;
+  if (p.Bt > B) p.Bt = B;
+  p.Tp2 = (Tq + 1) / 2;
+  if (mode == 0) {
+    if (a.s == 1) p.rows_alloc = (a.K - 1) * p.Bt + 128;
+    else {
+      const int need = (p.Tp2 + (a.K - 1) / 2) * p.Bt + 128;
+      p.rows_alloc = 2 * p.Tp2 * p.Bt > need ? 2 * p.Tp2 * p.Bt : need;
+    }
+    const int fill = (a.s == 1) ? Tq * p.Bt : 2 * p.Tp2 * p.Bt;
+    if (fill > p.rows_alloc) p.rows_alloc = fill;
+  } else {
+    p.rows_alloc = (a.K - 1) * p.Bt + 128;
+    const int fill = (Tq + a.K - 1) * p.Bt;
+    if (fill > p.rows_alloc) p.rows_alloc = fill;
+  }
+  p.rows_alloc = rup(p.rows_alloc, 8);
+  if (p.rows_alloc * 16 >= (1 << 18)) return false;
+  p.a_bytes = 2 * p.rows_alloc * 16;
+  const int mtiles = (B + p.Bt - 1) / p.Bt;
+  const int budget = 200 * 1024;
+  // neighbour structure on the host (fprop: nb lists; dgrad: transpose)
+  std::vector<std::vector<int>> lists(a.J);
+  for (int j = 0; j < a.J; ++j)
+    for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m) {
+      if (mode == 0) lists[j].push_back(plan->nb_idx[m]);
+      else lists[plan->nb_idx[m]].push_back(j);
+    }
+  int best = -1, best_nb = 0, best_stages = 0;
+  int gj_max = 512 / p.n_pad;
+  if (gj_max > a.J) gj_max = a.J;
+  if (gj_max > TC_MAX_GJ) gj_max = TC_MAX_GJ;
+  for (int GJ = gj_max; GJ >= 1; --GJ) {
+    int nbmax = 0;
+    for (int g0 = 0; g0 < a.J; g0 += GJ) {
+      std::vector<int> cnt(a.J, 0);
+      for (int j = g0; j < a.J && j < g0 + GJ; ++j)
+        for (int n : lists[j]) cnt[n]++;
+      for (int n = 0; n < a.J; ++n) nbmax = cnt[n] > nbmax ? cnt[n] : nbmax;
+    }
+    if (nbmax > TC_MAX_NB) continue;
+    const int stage = p.a_bytes + nbmax * a.K * p.n_pad * 32;
+    const int epi = GJ * p.n_real * 128 * 4;
+    int stages = budget / stage;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2 || epi > stages * stage) continue;
+    const int ctas = mtiles * ((a.J + GJ - 1) / GJ);
+    best = GJ; best_nb = nbmax; best_stages = stages;
+    if (ctas >= 96) break;       // largest group size that still fills most of the 148 SMs
+  }
+  if (best < 0) return false;
+  p.GJ = best; p.nbmax = best_nb; p.stages = best_stages;
+  p.stage_bytes = rup(p.a_bytes + best_nb * a.K * p.n_pad * 32, 128);
+  int cols = best * p.n_pad, pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  p.tmem_cols = pow2;
+  if (pow2 > 512) return false;
+  *out = p;
+  return true;
+}
+
+bool conv_tc_supported(const hmvae_conv_plan* plan, int B, int T, int mode) {
+  TcArgs p;
+  return tc_geometry(plan, B, T, mode, &p);
+}
+
+void conv_packed_sizes(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad) {
+  const ConvArgs& a = plan->a;
+  *n_fprop = (long)a.nnz * a.K * rup(a.ci, 8) * rup(a.co, 16);
+  *n_dgrad = (long)a.nnz * a.K * rup(a.co, 8) * rup(a.ci, 16);
+}
+
+int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* wp_d, cudaStream_t st) {
+  const ConvArgs& a = plan->a;
+  long nf, nd;
+  conv_packed_sizes(plan, &nf, &nd);
+  const long cap = (long)num_sms() * 16;
+  if (wp_f) {
+    long blocks = (nf + 255) / 256;
+    conv_pack_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, w, wp_f, 0, rup(a.co, 16), rup(a.ci, 8), nf);
+    int rc = check_launch("conv_pack(fprop)");
+    if (rc) return rc;
+  }
+  if (wp_d) {
+    long blocks = (nd + 255) / 256;
+    conv_pack_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, w, wp_d, 1, rup(a.ci, 16), rup(a.co, 8), nd);
+    int rc = check_launch("conv_pack(dgrad)");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, const float* wp,
+                   const float* bias, float* dst, int B, int T, cudaStream_t st) {
+  TcArgs p;
+  if (!tc_geometry(plan, B, T, mode, &p)) return fail_arg("conv (tcgen05): unsupported geometry");
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((B + p.Bt - 1) / p.Bt, (p.a.J + p.GJ - 1) / p.GJ);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, src, yact, wp, bias, dst);
+  return check_launch(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
+}
+
 }  // namespace hmvae

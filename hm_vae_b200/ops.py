@@ -61,6 +61,37 @@ class ConvPlan:
                 pass
 
 
+_force_repack = False
+
+
+class PackedWeights:
+    """Derived cache of a conv weight for the tcgen05 kernels: tf32-rounded, [block][tap][c/4][n_pad][4] for fprop and the
+    role-swapped layout for dgrad.  Re-packed (one kernel) whenever the dense parameter's version / storage changes."""
+
+    def __init__(self, plan):
+        nf, nd = ctypes.c_long(), ctypes.c_long()
+        check(lib.hmvae_conv_packed_size(plan.handle, ctypes.byref(nf), ctypes.byref(nd)), "conv_packed_size")
+        self.plan, self.nf, self.nd = plan, nf.value, nd.value
+        self.wp_f = self.wp_d = None
+        self.key = None
+
+    def get(self, weight):
+        key = (weight._version, weight.data_ptr())
+        if self.wp_f is None or self.wp_f.device != weight.device:
+            self.wp_f = torch.empty(self.nf, device=weight.device, dtype=torch.float32)
+            self.wp_d = torch.empty(self.nd, device=weight.device, dtype=torch.float32)
+            self.key = None
+        if key != self.key or _force_repack:
+            check(lib.hmvae_conv_pack_weights(self.plan.handle, ptr(weight.detach()), ptr(self.wp_f), ptr(self.wp_d), stream()),
+                  "conv_pack_weights")
+            self.key = key
+        return self.wp_f, self.wp_d
+
+
+def _tc_ok(plan, b, t_in, mode):
+    return _conv_impl != IMPL_SIMT and bool(lib.hmvae_conv_tc_supported(plan.handle, b, t_in, mode))
+
+
 class _SkeletonConvFn(Function):
     """y = epilogue(conv1d(pad(prologue(x)), W (.) mask, b)) -- skeleton.py:95-105 plus the fused neighbours."""
 
@@ -77,8 +108,20 @@ class _SkeletonConvFn(Function):
         else:
             y = torch.empty(shape, device=x.device, dtype=torch.float32)
         w = weight.contiguous()
-        check(lib.hmvae_conv_fprop(plan.handle, ptr(x), ptr(w), ptr(bias), ptr(y), b, t_in, _conv_impl, stream()), "conv_fprop")
+        tc_f, tc_d = _tc_ok(plan, b, t_in, 0), _tc_ok(plan, b, t_in, 1)
+        if _conv_impl == IMPL_TC and not tc_f:
+            raise _lib.HmvaeError("conv_fprop: the tcgen05 path does not support this geometry")
+        wp_d = None
+        if tc_f or tc_d:
+            if not hasattr(plan, "packed"):
+                plan.packed = PackedWeights(plan)
+            wp_f, wp_d = plan.packed.get(w)
+        if tc_f:
+            check(lib.hmvae_conv_fprop_tc(plan.handle, ptr(x), ptr(wp_f), ptr(bias), ptr(y), b, t_in, stream()), "conv_fprop_tc")
+        else:
+            check(lib.hmvae_conv_fprop(plan.handle, ptr(x), ptr(w), ptr(bias), ptr(y), b, t_in, _conv_impl, stream()), "conv_fprop")
         ctx.plan, ctx.t_in, ctx.has_bias = plan, t_in, bias is not None
+        ctx.wp_d = wp_d if tc_d else None
         ctx.save_for_backward(x, w, y if plan.lrelu else None)
         return y
 
@@ -92,7 +135,10 @@ class _SkeletonConvFn(Function):
         if ctx.needs_input_grad[0]:
             cin = plan.joints * plan.ci
             gxin = torch.empty((b, cin, t_in), device=x.device, dtype=torch.float32)
-            check(lib.hmvae_conv_dgrad(plan.handle, ptr(gy), ptr(y), ptr(w), ptr(gxin), b, t_in, _conv_impl, stream()), "conv_dgrad")
+            if ctx.wp_d is not None:
+                check(lib.hmvae_conv_dgrad_tc(plan.handle, ptr(gy), ptr(y), ptr(ctx.wp_d), ptr(gxin), b, t_in, stream()), "conv_dgrad_tc")
+            else:
+                check(lib.hmvae_conv_dgrad(plan.handle, ptr(gy), ptr(y), ptr(w), ptr(gxin), b, t_in, _conv_impl, stream()), "conv_dgrad")
             if plan.has_prologue:
                 gx = torch.empty_like(x)
                 check(lib.hmvae_conv_prologue_bwd(plan.handle, ptr(gxin), None, ptr(gx), b, t_in, stream()), "conv_prologue_bwd")
@@ -411,9 +457,16 @@ class FusedAdam:
             arr[i] = _lib.AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
         return arr, len(live)
 
+    def _bump_versions(self):
+        # the kernels update parameters through raw pointers: tell autograd / the packed-weight caches
+        for p in self.params:
+            if p.grad is not None:
+                torch.autograd.graph.increment_version(p)
+
     def step(self, grad_scale=1.0, lr=None, step=None):
         self.step_count = self.step_count + 1 if step is None else step
         arr, n = self._pack()
+        self._bump_versions()
         check(lib.hmvae_adam_step(arr, n, self.param_groups[0]["lr"] if lr is None else lr, self.betas[0], self.betas[1],
                                   self.eps, self.weight_decay, self.step_count, grad_scale, stream()), "adam_step")
 
@@ -437,6 +490,7 @@ class FusedAdam:
         host, dev = self.dyn_buffers(self.params[0].device)
         dev.copy_(host, non_blocking=True)
         arr, n = self._pack()
+        self._bump_versions()
         check(lib.hmvae_adam_step_dyn(arr, n, ptr(dev), self.betas[0], self.betas[1], self.eps, self.weight_decay, grad_scale,
                                       stream()), "adam_step_dyn")
 

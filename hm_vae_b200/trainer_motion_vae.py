@@ -151,8 +151,12 @@ class Trainer(nn.Module):
         self.gen_opt.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
         n0 = ops._lib.launch_count()
-        with torch.cuda.graph(graph):
-            static_out = self._device_step(static_in, hp, iterations)
+        ops._force_repack = True            # the packed tf32 weight copies must be refreshed inside every replay
+        try:
+            with torch.cuda.graph(graph):
+                static_out = self._device_step(static_in, hp, iterations)
+        finally:
+            ops._force_repack = False
         self.launches_per_step = ops._lib.launch_count() - n0
         self._graphs[self._graph_key(hp, iterations, data)] = (graph, static_in, static_out)
         return graph

@@ -77,6 +77,17 @@ int hmvae_conv_dgrad(const hmvae_conv_plan* plan, const float* dy, const float* 
  * which must be 0).  dbias may be NULL.  accumulate != 0 adds into dw/dbias. */
 int hmvae_conv_wgrad(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* y, float* dw,
                      float* dbias, int batch, int t_in, int accumulate, int impl, void* stream);
+/* ---- tensor-core (tcgen05, TF32 operands, FP32 accumulation in TMEM) variants.  They read a packed, tf32-rounded
+ * copy of the weights; refresh it with hmvae_conv_pack_weights whenever the dense parameter changes.
+ * mode: 0 = fprop, 1 = dgrad.  hmvae_conv_tc_supported returns 1 when (plan, batch, t_in) maps onto the kernel. */
+int hmvae_conv_tc_supported(const hmvae_conv_plan* plan, int batch, int t_in, int mode);
+int hmvae_conv_packed_size(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad);   /* floats */
+int hmvae_conv_pack_weights(const hmvae_conv_plan* plan, const float* w, float* wp_fprop, float* wp_dgrad, void* stream);
+int hmvae_conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float* wp_fprop, const float* bias, float* y,
+                        int batch, int t_in, void* stream);
+int hmvae_conv_dgrad_tc(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* wp_dgrad, float* dxin,
+                        int batch, int t_in, void* stream);
+
 /* adjoint of the prologue: dsrc[B, src_joints*ci, T_src] from dxin[B, J*ci, T]; if src_act != NULL the result is
  * multiplied by lrelu'(src_act) (src_act = the activation tensor that fed this layer). */
 int hmvae_conv_prologue_bwd(const hmvae_conv_plan* plan, const float* dxin, const float* src_act, float* dsrc,
