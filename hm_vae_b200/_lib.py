@@ -70,8 +70,9 @@ _SIGS = {
     "hmvae_conv_tc_supported": (c_int, [P, c_int, c_int, c_int]),
     "hmvae_conv_packed_size": (c_int, [P, POINTER(c_long), POINTER(c_long)]),
     "hmvae_conv_pack_weights": (c_int, [P, P, P, P, P]),
-    "hmvae_conv_fprop_tc": (c_int, [P, P, P, P, P, c_int, c_int, P]),
-    "hmvae_conv_dgrad_tc": (c_int, [P, P, P, P, P, c_int, c_int, P]),
+    "hmvae_conv_tc_workspace": (c_long, [P, c_int, c_int, c_int]),
+    "hmvae_conv_fprop_tc": (c_int, [P, P, P, P, P, c_int, c_int, P, c_long, P]),
+    "hmvae_conv_dgrad_tc": (c_int, [P, P, P, P, P, c_int, c_int, P, c_long, P]),
     "hmvae_pool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, IP, IP, c_int, P]),
     "hmvae_pool_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, IP, IP, c_int, P]),
     "hmvae_unpool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, IP, P]),

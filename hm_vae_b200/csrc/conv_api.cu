@@ -23,7 +23,8 @@ bool conv_tc_supported(const hmvae_conv_plan* plan, int B, int T, int mode);
 void conv_packed_sizes(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad);
 int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* wp_d, cudaStream_t st);
 int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, const float* wp,
-                   const float* bias, float* dst, int B, int T, cudaStream_t st);
+                   const float* bias, float* dst, int B, int T, void* workspace, long workspace_bytes, cudaStream_t st);
+long conv_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T, int mode);
 }  // namespace hmvae
 
 using namespace hmvae;
@@ -141,22 +142,27 @@ extern "C" int hmvae_conv_pack_weights(const hmvae_conv_plan* plan, const float*
   return conv_pack(plan, w, wp_fprop, wp_dgrad, (cudaStream_t)stream);
 }
 
+extern "C" long hmvae_conv_tc_workspace(const hmvae_conv_plan* plan, int batch, int t_in, int mode) {
+  if (!plan || batch < 1 || t_in < 1 || (mode != 0 && mode != 1)) return -1;
+  return conv_tc_workspace_bytes(plan, batch, t_in, mode);
+}
+
 extern "C" int hmvae_conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float* wp_fprop, const float* bias,
-                                   float* y, int batch, int t_in, void* stream) {
+                                   float* y, int batch, int t_in, void* workspace, long workspace_bytes, void* stream) {
   int rc = check_shape(plan, batch, t_in, "conv_fprop_tc");
   if (rc) return rc;
   if (!x || !wp_fprop || !y) return fail_arg("conv_fprop_tc: null pointer");
   if (batch == 0) return 0;
-  return conv_tc_launch(plan, 0, x, nullptr, wp_fprop, bias, y, batch, t_in, (cudaStream_t)stream);
+  return conv_tc_launch(plan, 0, x, nullptr, wp_fprop, bias, y, batch, t_in, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int hmvae_conv_dgrad_tc(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* wp_dgrad,
-                                   float* dxin, int batch, int t_in, void* stream) {
+                                   float* dxin, int batch, int t_in, void* workspace, long workspace_bytes, void* stream) {
   int rc = check_shape(plan, batch, t_in, "conv_dgrad_tc");
   if (rc) return rc;
   if (!dy || !wp_dgrad || !dxin || (plan->d.lrelu && !y)) return fail_arg("conv_dgrad_tc: null pointer");
   if (batch == 0) return 0;
-  return conv_tc_launch(plan, 1, dy, y, wp_dgrad, nullptr, dxin, batch, t_in, (cudaStream_t)stream);
+  return conv_tc_launch(plan, 1, dy, y, wp_dgrad, nullptr, dxin, batch, t_in, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int hmvae_conv_dgrad(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* w, float* dxin,

@@ -2,27 +2,34 @@
 //
 // "Shift-GEMM" formulation (conv).  For one output joint j and one input joint n in its neighbour list
 //     D_j[m, o] += sum_k  A_n[m + shift(k), c] * W_{j,n,k}[o, c]
-// where the rows of A are (time, sequence) pairs laid out time-major/sequence-minor in shared memory, 16 bytes
-// (4 tf32 channels) per row and per K-chunk.  In the canonical no-swizzle K-major UMMA layout (8-row core matrices
-// packed back to back, SBO = 128 B, LBO = chunk stride) the operand for tap k is the SAME tile with its start address
-// advanced by shift(k) rows, so no im2col expansion is ever materialised: one staged activation tile feeds all K taps
-// and every output joint that has n as a neighbour.  Masked (j, n) blocks are never visited.
+// where the rows of A are (time, sequence) pairs laid out time-major/sequence-minor, 16 bytes (4 tf32 channels) per row
+// and per K-chunk.  In the canonical no-swizzle K-major UMMA layout (8-row core matrices packed back to back,
+// SBO = 128 B, LBO = chunk stride) the operand for tap k is the SAME tile with its start address advanced by shift(k)
+// rows, so no im2col expansion is ever materialised: one staged activation tile feeds all K taps and every output joint
+// that has n as a neighbour.  Masked (j, n) blocks are never visited.
 //   * fprop : rows = (t_out, b); stride-2 layers keep even/odd input phases in two row ranges so taps stay shifts.
 //   * dgrad : same kernel with the roles of the channel sets swapped, transposed neighbour lists, flipped taps and a
-//             zero-inserting loader (stride 2); the reflect-padding adjoint is folded in the epilogue.
-// Weights come from a packed, tf32-rounded copy ([block][tap][c/4][n_pad][4]) refreshed by hmvae_conv_pack_weights
-// whenever the dense parameter changes, and are moved with 1-D bulk (TMA) copies.
+//             zero-inserting staging pass (stride 2); the reflect-padding adjoint is folded in the epilogue.
 //
-// Warp roles (192 threads): warp 0 = weight producer (cp.async.bulk + mbarrier expect_tx), warp 1 = TMEM allocator and
-// single-thread MMA issuer, warps 2-5 = activation producers (global -> tf32 -> smem, with the fused pad / upsample /
-// unpool / lrelu' index math), then the epilogue (tcgen05.ld -> smem transpose -> coalesced store with bias / LeakyReLU /
-// reflect fold).  smem stages cycle through full/empty mbarriers; tcgen05.commit releases a stage.
+// Two kernels per conv:
+//   1. conv_tc_prep_kernel  -- elementwise gather: applies reflect/zero padding, the decoder's x2 linear upsample and unpool
+//      (fprop) or zero-insertion and LeakyReLU' (dgrad), rounds to tf32 and writes activation tiles to a staging buffer in
+//      EXACTLY the shared-memory layout the MMA wants.  (HBM/L2-bound; its output stays L2-resident.)
+//   2. conv_tc_kernel       -- pure TMA-fed tensor-core kernel.  Warp 0: one thread arms an mbarrier with expect_tx and issues
+//      1-D bulk copies (cp.async.bulk) of the activation tile and of the packed weight pieces; warp 1: TMEM allocation and
+//      single-thread tcgen05.mma issue, tcgen05.commit releases the smem stage; warps 2-5: epilogue (tcgen05.ld -> smem
+//      transpose -> coalesced store with bias / LeakyReLU / reflect fold).
+// Weights come from a packed, tf32-rounded copy ([block][K-chunk cb][tap][c/4][n_pad][4], i.e. one contiguous piece per
+// pipeline stage and joint) refreshed by hmvae_conv_pack_weights.  Layers whose (tile, joint-group) grid cannot fill the
+// 148 SMs (small B*T, big channel counts) are additionally split along the reduction (neighbour joints x channel blocks)
+// over gridDim.z; the partial sums go to a workspace and conv_tc_finish_kernel adds them in a fixed order (deterministic)
+// together with bias / LeakyReLU.
 #include "conv_common.cuh"
 
 namespace hmvae {
 
 constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_MAX_GJ = 32;
 constexpr int TC_MAX_NB = 16;
 
@@ -33,13 +40,15 @@ struct TcArgs {
   const int* idx;
   int n_real, n_pad;   // N-side channels per joint (real, padded to 16)
   int ck, ck_pad;      // reduction channels per K-side joint (real, padded to 8)
+  int KC;              // reduction channels per pipeline stage (multiple of 8, divides ck_pad)
   int Bt, Tt;          // sequences per tile, rows-per-sequence (M = Tt*Bt <= 128)
-  int rows_alloc;      // smem rows per 16-byte chunk column
+  int rows_alloc;      // rows per 16-byte chunk column of an activation tile
   int Tp2;             // fprop stride 2: rows per phase / Bt
   int GJ, nbmax, stages;
-  int B, T, T_out;
+  int B, T, T_out, mtiles;
   int a_bytes, stage_bytes;
   int tmem_cols;
+  int splits, split_len;   // split-K: gridDim.z CTAs per (tile, group), each handles split_len consecutive stages
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -89,23 +98,24 @@ __device__ __forceinline__ long tc_out_index(const ConvArgs& a, long b, int j, i
 // wp[block][k][q][n_pad][4]:  fprop: block = CSR position (j, n), rows = out channels o, cols = in channels c.
 //                             dgrad: block = transposed-CSR position (n, j), rows = in channels c, cols = out channels o.
 __global__ void conv_pack_kernel(ConvArgs a, const float* __restrict__ w, float* __restrict__ wp, int mode, int n_pad,
-                                 int ck_pad, long total) {
+                                 int ck_pad, int KC, long total) {
   const int Cin = a.J * a.ci;
   const int per_blk = a.K * ck_pad * n_pad;
+  const int qpb = KC / 4;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int blk = (int)(e / per_blk);
     int r = (int)(e % per_blk);
     const int c4 = r & 3; r >>= 2;
     const int row = r % n_pad; r /= n_pad;
-    const int q = r % (ck_pad / 4);
-    const int k = r / (ck_pad / 4);
-    const int col = q * 4 + c4;
+    const int h = r % qpb; r /= qpb;
+    const int k = r % a.K;
+    const int cb = r / a.K;
+    const int col = (cb * qpb + h) * 4 + c4;
     float v = 0.f;
     if (mode == 0) {
       const int j = a.blk_j[blk], n = a.blk_n[blk];
       if (row < a.co && col < a.ci) v = w[((long)(j * a.co + row) * Cin + n * a.ci + col) * a.K + k];
     } else {
-      // transposed CSR: find (n, j) of this block
       int n = 0;
       while (a.nbT_off[n + 1] <= blk) ++n;
       const int j = a.nbT_idx[blk];
@@ -115,15 +125,66 @@ __global__ void conv_pack_kernel(ConvArgs a, const float* __restrict__ w, float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------- activation staging
+// astage[mt][n][cb][h][rows_alloc][4]  (cb = KC-channel block, h = 16-byte chunk inside the block)
+__global__ void __launch_bounds__(256) conv_tc_prep_kernel(TcArgs p, const float* __restrict__ src,
+                                                           const float* __restrict__ yact, float4* __restrict__ astage) {
+  const ConvArgs& a = p.a;
+  const int Tq = p.T + 2 * a.p;
+  const int tfill = (p.mode == 0) ? Tq : (Tq + a.K - 1);
+  const int nq = p.ck_pad / 4;             // 16-byte chunks per K-side joint
+  const int qpb = p.KC / 4;                // chunks per stage block
+  const long per_mt = (long)a.J * nq * p.Bt * tfill;
+  const long total = per_mt * p.mtiles;
+  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(it % tfill);
+    long rest = it / tfill;
+    const int b = (int)(rest % p.Bt); rest /= p.Bt;
+    const int q = (int)(rest % nq); rest /= nq;
+    const int n = (int)(rest % a.J);
+    const int mt = (int)(rest / a.J);
+    const long bb = (long)mt * p.Bt + b;
+    const int c0 = q * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    int row;
+    if (p.mode == 0) {
+      row = (a.s == 1) ? r * p.Bt + b : ((r & 1) * p.Tp2 + (r >> 1)) * p.Bt + b;
+      if (bb < p.B) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (c0 + i < a.ci) v[i] = load_padded(src, a, bb, n, c0 + i, r, p.T);
+      }
+    } else {
+      row = r * p.Bt + b;
+      const int zz = r - (a.K - 1);
+      if (bb < p.B && zz >= 0 && (zz % a.s) == 0 && zz / a.s < p.T_out) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (c0 + i < a.co) {
+            const long oi = tc_out_index(a, bb, n, c0 + i, zz / a.s, p.T_out);
+            float t = src[oi];
+            if (a.lrelu && !(yact[oi] > 0.f)) t *= 0.2f;
+            v[i] = t;
+          }
+      }
+    }
+    float4 o;
+    o.x = __uint_as_float(to_tf32(v[0])); o.y = __uint_as_float(to_tf32(v[1]));
+    o.z = __uint_as_float(to_tf32(v[2])); o.w = __uint_as_float(to_tf32(v[3]));
+    const int cb = q / qpb, h = q % qpb;
+    astage[((((long)mt * a.J + n) * (nq / qpb) + cb) * qpb + h) * p.rows_alloc + row] = o;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- main kernel
 struct TcWork {
+  unsigned int started;
   int cnt[64];
   unsigned char jl[64][TC_MAX_NB];
   int blk[64][TC_MAX_NB];
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const float* __restrict__ src,
-                                                                const float* __restrict__ yact,
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const unsigned char* __restrict__ astage,
                                                                 const float* __restrict__ wp,
                                                                 const float* __restrict__ bias, float* __restrict__ dst) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -133,16 +194,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
 
   const ConvArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = blockIdx.y;
-  const int j0 = g * p.GJ;
+  const int mt = blockIdx.x;
+  const int j0 = blockIdx.y * p.GJ;
   const int gj = (a.J - j0 < p.GJ) ? a.J - j0 : p.GJ;
-  const int b0 = blockIdx.x * p.Bt;
-  const int ncb = p.ck_pad / 8;
+  const int b0 = mt * p.Bt;
+  const int ncb = p.ck_pad / p.KC;
+  const int qpb = p.KC / 4;
 
-  // ---- setup: barriers, TMEM, per-CTA work table
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1 + 4);
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&accum_bar, 1);
@@ -170,27 +231,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-
-  const int rows_alloc = p.rows_alloc;
-  const int blk_floats = a.K * p.ck_pad * p.n_pad;
+  const uint32_t tap_bytes = (uint32_t)qpb * p.n_pad * 16;   // one tap of a weight piece: qpb chunks x n_pad rows x 16 B
+  const uint32_t piece = (uint32_t)a.K * tap_bytes;          // one (slot) weight piece of a stage: all K taps, contiguous
+  const int si_beg = blockIdx.z * p.split_len, si_end = si_beg + p.split_len;
 
   if (warp == 0) {
-    // =============================== weight producer (bulk copies) ===============================
-    int s = 0;
+    // =============================== producer: bulk copies of activation tile + weight pieces ===============================
+    int s = 0, si = 0;
     uint32_t ph = 0;
     for (int n = 0; n < a.J; ++n) {
       const int cnt = work.cnt[n];
       if (cnt == 0) continue;
-      for (int cb = 0; cb < ncb; ++cb) {
+      for (int cb = 0; cb < ncb; ++cb, ++si) {
+        if (si < si_beg || si >= si_end) continue;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        unsigned char* bsm = smem_raw + (size_t)s * p.stage_bytes + p.a_bytes;
-        const uint32_t piece = (uint32_t)p.n_pad * 32;       // 2 chunks x n_pad rows x 16 B
-        if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)cnt * a.K * piece);
+        unsigned char* st = smem_raw + (size_t)s * p.stage_bytes;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.a_bytes + (uint32_t)cnt * piece);
+          bulk_g2s(st, astage + (((size_t)mt * a.J + n) * ncb + cb) * p.a_bytes, (uint32_t)p.a_bytes, &full_bar[s]);
+        }
         __syncwarp();
-        for (int e = lane; e < cnt * a.K; e += 32) {
-          const int slot = e / a.K, k = e % a.K;
-          const float* gsrc = wp + (size_t)work.blk[n][slot] * blk_floats + ((size_t)k * (p.ck_pad / 4) + cb * 2) * p.n_pad * 4;
-          bulk_g2s(bsm + (size_t)(slot * a.K + k) * piece, gsrc, piece, &full_bar[s]);
+        if (lane < cnt) {
+          const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(wp) + ((size_t)work.blk[n][lane] * ncb + cb) * piece;
+          bulk_g2s(st + p.a_bytes + (size_t)lane * piece, gsrc, piece, &full_bar[s]);
         }
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
@@ -198,30 +261,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
-    int s = 0;
+    int s = 0, si = 0;
     uint32_t ph = 0, started = 0;
     for (int n = 0; n < a.J; ++n) {
       const int cnt = work.cnt[n];
       if (cnt == 0) continue;
-      for (int cb = 0; cb < ncb; ++cb) {
+      for (int cb = 0; cb < ncb; ++cb, ++si) {
+        if (si < si_beg || si >= si_end) continue;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_base = smem_u32(smem_raw + (size_t)s * p.stage_bytes);
           const uint32_t b_base = a_base + p.a_bytes;
-          const uint32_t piece = (uint32_t)p.n_pad * 32;
           for (int e = 0; e < cnt; ++e) {
             const int jl = work.jl[n][e];
             const uint32_t d_addr = tmem_base + (uint32_t)(jl * p.n_pad);
+            uint32_t acc = (started >> jl) & 1u;
             for (int k = 0; k < a.K; ++k) {
               int shift;
               if (p.mode == 0) shift = (a.s == 1) ? k * p.Bt : ((k & 1) * p.Tp2 + (k >> 1)) * p.Bt;
               else shift = (a.K - 1 - k) * p.Bt;
-              const uint64_t adesc = tc_desc(a_base + (uint32_t)shift * 16, (uint32_t)rows_alloc * 16, 128);
-              const uint64_t bdesc = tc_desc(b_base + (uint32_t)(e * a.K + k) * piece, (uint32_t)p.n_pad * 16, 128);
-              tc_mma_tf32(d_addr, adesc, bdesc, idesc, (started >> jl) & 1u);
-              started |= 1u << jl;
+              const uint32_t a_k = a_base + (uint32_t)shift * 16;
+              const uint32_t b_k = b_base + (uint32_t)e * piece + (uint32_t)k * tap_bytes;
+              for (int kk = 0; kk < qpb / 2; ++kk) {       // one MMA per 8 reduction channels (2 chunks)
+                const uint64_t adesc = tc_desc(a_k + (uint32_t)kk * 2 * p.rows_alloc * 16, (uint32_t)p.rows_alloc * 16, 128);
+                const uint64_t bdesc = tc_desc(b_k + (uint32_t)kk * 2 * p.n_pad * 16, (uint32_t)p.n_pad * 16, 128);
+                tc_mma_tf32(d_addr, adesc, bdesc, idesc, acc);
+                acc = 1;
+              }
             }
+            started |= 1u << jl;
           }
           tc_commit(&empty_bar[s]);
         }
@@ -229,71 +298,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
-    if (lane == 0) tc_commit(&accum_bar);
+    if (lane == 0) {
+      work.started = started;
+      __threadfence_block();
+      tc_commit(&accum_bar);
+    }
     __syncwarp();
   } else {
-    // =============================== activation producers (warps 2..5) ===============================
+    // =============================== epilogue (warps 2..5) ===============================
     const int pt = tid - 64;            // 0..127
-    int s = 0;
-    uint32_t ph = 0;
-    const int Tq = p.T + 2 * a.p;
-    const int tfill = (p.mode == 0) ? Tq : (Tq + a.K - 1);
-    for (int n = 0; n < a.J; ++n) {
-      if (work.cnt[n] == 0) continue;
-      for (int cb = 0; cb < ncb; ++cb) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        float4* asm4 = reinterpret_cast<float4*>(smem_raw + (size_t)s * p.stage_bytes);
-        const int items = 2 * p.Bt * tfill;
-        for (int it = pt; it < items; it += 128) {
-          const int r = it % tfill;
-          const int hb = it / tfill;
-          const int b = hb % p.Bt, h = hb / p.Bt;
-          const int c0 = cb * 8 + h * 4;
-          const long bb = b0 + b;
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
-          int row;
-          if (p.mode == 0) {
-            row = (a.s == 1) ? r * p.Bt + b : ((r & 1) * p.Tp2 + (r >> 1)) * p.Bt + b;
-            if (bb < p.B) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (c0 + i < a.ci) v[i] = load_padded(src, a, bb, n, c0 + i, r, p.T);
-            }
-          } else {
-            row = r * p.Bt + b;
-            const int zz = r - (a.K - 1);
-            if (bb < p.B && zz >= 0 && (zz % a.s) == 0 && zz / a.s < p.T_out) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (c0 + i < a.co) {
-                  const long oi = tc_out_index(a, bb, n, c0 + i, zz / a.s, p.T_out);
-                  float t = src[oi];
-                  if (a.lrelu && !(yact[oi] > 0.f)) t *= 0.2f;
-                  v[i] = t;
-                }
-            }
-          }
-          float4 o;
-          o.x = __uint_as_float(to_tf32(v[0])); o.y = __uint_as_float(to_tf32(v[1]));
-          o.z = __uint_as_float(to_tf32(v[2])); o.w = __uint_as_float(to_tf32(v[3]));
-          asm4[(size_t)h * rows_alloc + row] = o;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
-      }
-    }
-    // =============================== epilogue ===============================
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     float* outs = reinterpret_cast<float*>(smem_raw);          // [gj * n_real][128]   (stage buffers are free now)
     const int lq = warp & 3;
     const int m = lq * 32 + lane;
+    const unsigned int started = *reinterpret_cast<volatile unsigned int*>(&work.started);
     for (int jl = 0; jl < gj; ++jl) {
       for (int c16 = 0; c16 < p.n_pad; c16 += 16) {
         float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(jl * p.n_pad + c16), v);
+        if ((started >> jl) & 1u) {
+          tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(jl * p.n_pad + c16), v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (c16 + i < p.n_real) outs[(size_t)(jl * p.n_real + c16 + i) * 128 + m] = v[i];
@@ -302,7 +330,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
     tc_fence_before();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int nch = gj * p.n_real;
-    if (p.mode == 0) {
+    if (p.splits > 1) {
+      // partial sums: plain [split][B][J*n_real][Tr] layout (Tr = T_out for fprop, T for dgrad), finished by conv_tc_finish_kernel
+      const int Tr = (p.mode == 0) ? p.T_out : p.T;
+      float* part = dst + (size_t)blockIdx.z * p.B * a.J * p.n_real * Tr;
+      const int total = nch * p.Bt * Tr;
+      for (int e = pt; e < total; e += 128) {
+        const int u = e % Tr;
+        const int r = e / Tr;
+        const int b = r % p.Bt, ch = r / p.Bt;
+        if (b0 + b < p.B) {
+          float v;
+          if (p.mode == 0) {
+            v = outs[(size_t)ch * 128 + u * p.Bt + b];
+          } else {
+            const float* row = outs + (size_t)ch * 128 + b;
+            v = row[(u + a.p) * p.Bt];
+            if (a.pad_mode == 1) {
+              if (u >= 1 && u <= a.p) v += row[(a.p - u) * p.Bt];
+              if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += row[(a.p + 2 * (p.T - 1) - u) * p.Bt];
+            }
+          }
+          part[((size_t)(b0 + b) * a.J * p.n_real + (size_t)j0 * p.n_real + ch) * Tr + u] = v;
+        }
+      }
+    } else if (p.mode == 0) {
       const int total = nch * p.Bt * p.T_out;
       for (int e = pt; e < total; e += 128) {
         const int t = e % p.T_out;
@@ -343,8 +395,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- split-K finish
+__global__ void conv_tc_finish_kernel(TcArgs p, const float* __restrict__ part, const float* __restrict__ bias,
+                                      float* __restrict__ dst) {
+  const ConvArgs& a = p.a;
+  const int Tr = (p.mode == 0) ? p.T_out : p.T;
+  const int C = a.J * p.n_real;
+  const long per = (long)p.B * C * Tr;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int z = 0; z < p.splits; ++z) v += part[z * per + e];
+    if (p.mode == 0) {
+      const int t = (int)(e % Tr);
+      const long r = e / Tr;
+      const int ch = (int)(r % C);
+      const long b = r / C;
+      const int j = ch / p.n_real, o = ch % p.n_real;
+      if (bias) v += bias[ch];
+      if (a.lrelu) v = lrelu_f(v, 0.2f);
+      dst[tc_out_index(a, b, j, o, t, p.T_out)] = v;
+    } else {
+      dst[e] = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 static inline int rup(int v, int m) { return (v + m - 1) / m * m; }
+
+// reduction channels per stage: a property of the layer (the packed weight layout depends on it), not of the batch
+static int tc_pick_kc(int ck_pad, int n_pad, int K) {
+  const int kcs[4] = {32, 24, 16, 8};
+  for (int i = 0; i < 4; ++i)
+    if (ck_pad % kcs[i] == 0 && K * (kcs[i] / 4) * n_pad * 16 <= 32 * 1024) return kcs[i];
+  return 8;
+}
 
 static bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out) {
   const ConvArgs& a = plan->a;
@@ -387,21 +472,21 @@ static bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcA
   }
   p.rows_alloc = rup(p.rows_alloc, 8);
   if (p.rows_alloc * 16 >= (1 << 18)) return false;
-  p.a_bytes = 2 * p.rows_alloc * 16;
-  const int mtiles = (B + p.Bt - 1) / p.Bt;
-  const int budget = 200 * 1024;
-  // neighbour structure on the host (fprop: nb lists; dgrad: transpose)
+  p.mtiles = (B + p.Bt - 1) / p.Bt;
+  const int budget = 208 * 1024;
+  p.KC = tc_pick_kc(p.ck_pad, p.n_pad, a.K);
+  p.a_bytes = (p.KC / 4) * p.rows_alloc * 16;
   std::vector<std::vector<int>> lists(a.J);
   for (int j = 0; j < a.J; ++j)
     for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m) {
       if (mode == 0) lists[j].push_back(plan->nb_idx[m]);
       else lists[plan->nb_idx[m]].push_back(j);
     }
-  int best = -1, best_nb = 0, best_stages = 0;
   int gj_max = 512 / p.n_pad;
   if (gj_max > a.J) gj_max = a.J;
   if (gj_max > TC_MAX_GJ) gj_max = TC_MAX_GJ;
-  for (int GJ = gj_max; GJ >= 1; --GJ) {
+  bool found = false;
+  for (int GJ = gj_max; GJ >= 1 && !found; --GJ) {
     int nbmax = 0;
     for (int g0 = 0; g0 < a.J; g0 += GJ) {
       std::vector<int> cnt(a.J, 0);
@@ -410,22 +495,41 @@ static bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcA
       for (int n = 0; n < a.J; ++n) nbmax = cnt[n] > nbmax ? cnt[n] : nbmax;
     }
     if (nbmax > TC_MAX_NB) continue;
-    const int stage = p.a_bytes + nbmax * a.K * p.n_pad * 32;
+    const int ctas = p.mtiles * ((a.J + GJ - 1) / GJ);
+    if (ctas < 96 && GJ > 1) continue;            // prefer filling the 148 SMs over sharing tiles inside a CTA
+    const int stage = rup(p.a_bytes + nbmax * a.K * (p.KC / 4) * p.n_pad * 16, 128);
     const int epi = GJ * p.n_real * 128 * 4;
     int stages = budget / stage;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2 || epi > stages * stage) continue;
-    const int ctas = mtiles * ((a.J + GJ - 1) / GJ);
-    best = GJ; best_nb = nbmax; best_stages = stages;
-    if (ctas >= 96) break;       // largest group size that still fills most of the 148 SMs
+    p.GJ = GJ; p.nbmax = nbmax; p.stages = stages; p.stage_bytes = stage;
+    found = true;
   }
-  if (best < 0) return false;
-  p.GJ = best; p.nbmax = best_nb; p.stages = best_stages;
-  p.stage_bytes = rup(p.a_bytes + best_nb * a.K * p.n_pad * 32, 128);
-  int cols = best * p.n_pad, pow2 = 32;
+  if (!found) return false;
+  {
+    // split-K: longest per-CTA stage sequence over the groups, cut so that the grid reaches ~2 CTAs per SM
+    int longest = 0;
+    for (int g0 = 0; g0 < a.J; g0 += p.GJ) {
+      std::vector<int> used(a.J, 0);
+      for (int j = g0; j < a.J && j < g0 + p.GJ; ++j)
+        for (int n : lists[j]) used[n] = 1;
+      int c = 0;
+      for (int n = 0; n < a.J; ++n) c += used[n];
+      c *= p.ck_pad / p.KC;
+      longest = c > longest ? c : longest;
+    }
+    const int ctas = p.mtiles * ((a.J + p.GJ - 1) / p.GJ);
+    int splits = (2 * 148 + ctas - 1) / ctas;
+    if (splits > longest / 2) splits = longest / 2;       // at least 2 stages per CTA
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+    p.split_len = (longest + splits - 1) / splits;
+    p.splits = (longest + p.split_len - 1) / p.split_len;
+  }
+  int cols = p.GJ * p.n_pad, pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
-  p.tmem_cols = pow2;
   if (pow2 > 512) return false;
+  p.tmem_cols = pow2;
   *out = p;
   return true;
 }
@@ -433,6 +537,18 @@ static bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcA
 bool conv_tc_supported(const hmvae_conv_plan* plan, int B, int T, int mode) {
   TcArgs p;
   return tc_geometry(plan, B, T, mode, &p);
+}
+
+static long tc_stage_ws(const TcArgs& p) { return (long)p.mtiles * p.a.J * (p.ck_pad / p.KC) * p.a_bytes; }
+static long tc_part_ws(const TcArgs& p) {
+  if (p.splits <= 1) return 0;
+  return (long)p.splits * p.B * p.a.J * p.n_real * (p.mode == 0 ? p.T_out : p.T) * 4;
+}
+
+long conv_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T, int mode) {
+  TcArgs p;
+  if (!tc_geometry(plan, B, T, mode, &p)) return -1;
+  return tc_stage_ws(p) + tc_part_ws(p);
 }
 
 void conv_packed_sizes(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad) {
@@ -448,13 +564,15 @@ int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* w
   const long cap = (long)num_sms() * 16;
   if (wp_f) {
     long blocks = (nf + 255) / 256;
-    conv_pack_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, w, wp_f, 0, rup(a.co, 16), rup(a.ci, 8), nf);
+    conv_pack_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, w, wp_f, 0, rup(a.co, 16), rup(a.ci, 8),
+                                                                         tc_pick_kc(rup(a.ci, 8), rup(a.co, 16), a.K), nf);
     int rc = check_launch("conv_pack(fprop)");
     if (rc) return rc;
   }
   if (wp_d) {
     long blocks = (nd + 255) / 256;
-    conv_pack_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, w, wp_d, 1, rup(a.ci, 16), rup(a.co, 8), nd);
+    conv_pack_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, w, wp_d, 1, rup(a.ci, 16), rup(a.co, 8),
+                                                                         tc_pick_kc(rup(a.co, 8), rup(a.ci, 16), a.K), nd);
     int rc = check_launch("conv_pack(dgrad)");
     if (rc) return rc;
   }
@@ -462,14 +580,32 @@ int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* w
 }
 
 int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, const float* wp,
-                   const float* bias, float* dst, int B, int T, cudaStream_t st) {
+                   const float* bias, float* dst, int B, int T, void* workspace, long workspace_bytes, cudaStream_t st) {
   TcArgs p;
   if (!tc_geometry(plan, B, T, mode, &p)) return fail_arg("conv (tcgen05): unsupported geometry");
+  const long need = tc_stage_ws(p) + tc_part_ws(p);
+  if (!workspace || workspace_bytes < need) return fail_arg("conv (tcgen05): workspace too small");
+  float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + tc_stage_ws(p));
+  if (!aligned16(workspace) || !aligned16(wp)) return fail_arg("conv (tcgen05): workspace / packed weights must be 16-byte aligned");
+  {
+    const int Tq = T + 2 * p.a.p;
+    const long items = (long)p.mtiles * p.a.J * (p.ck_pad / 4) * p.Bt * (mode == 0 ? Tq : Tq + p.a.K - 1);
+    long blocks = (items + 255) / 256, cap = (long)num_sms() * 8;
+    conv_tc_prep_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, src, yact, reinterpret_cast<float4*>(workspace));
+    int rc = check_launch("conv_tc_prep");
+    if (rc) return rc;
+  }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((B + p.Bt - 1) / p.Bt, (p.a.J + p.GJ - 1) / p.GJ);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, src, yact, wp, bias, dst);
-  return check_launch(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
+  dim3 grid(p.mtiles, (p.a.J + p.GJ - 1) / p.GJ, p.splits);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, reinterpret_cast<const unsigned char*>(workspace), wp, bias,
+                                                 p.splits > 1 ? part : dst);
+  int rc = check_launch(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
+  if (rc || p.splits <= 1) return rc;
+  const long per = (long)p.B * p.a.J * p.n_real * (mode == 0 ? p.T_out : p.T);
+  long blocks = (per + 255) / 256, cap = (long)num_sms() * 8;
+  conv_tc_finish_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, part, bias, dst);
+  return check_launch("conv_tc_finish");
 }
 
 }  // namespace hmvae

@@ -88,6 +88,11 @@ class PackedWeights:
         return self.wp_f, self.wp_d
 
 
+def _workspace(plan, b, t_in, mode, device):
+    n = int(lib.hmvae_conv_tc_workspace(plan.handle, b, t_in, mode))
+    return torch.empty((n + 3) // 4, device=device, dtype=torch.float32)
+
+
 def _tc_ok(plan, b, t_in, mode):
     return _conv_impl != IMPL_SIMT and bool(lib.hmvae_conv_tc_supported(plan.handle, b, t_in, mode))
 
@@ -117,7 +122,9 @@ class _SkeletonConvFn(Function):
                 plan.packed = PackedWeights(plan)
             wp_f, wp_d = plan.packed.get(w)
         if tc_f:
-            check(lib.hmvae_conv_fprop_tc(plan.handle, ptr(x), ptr(wp_f), ptr(bias), ptr(y), b, t_in, stream()), "conv_fprop_tc")
+            ws = _workspace(plan, b, t_in, 0, x.device)
+            check(lib.hmvae_conv_fprop_tc(plan.handle, ptr(x), ptr(wp_f), ptr(bias), ptr(y), b, t_in, ptr(ws), ws.numel() * 4, stream()),
+                  "conv_fprop_tc")
         else:
             check(lib.hmvae_conv_fprop(plan.handle, ptr(x), ptr(w), ptr(bias), ptr(y), b, t_in, _conv_impl, stream()), "conv_fprop")
         ctx.plan, ctx.t_in, ctx.has_bias = plan, t_in, bias is not None
@@ -136,7 +143,9 @@ class _SkeletonConvFn(Function):
             cin = plan.joints * plan.ci
             gxin = torch.empty((b, cin, t_in), device=x.device, dtype=torch.float32)
             if ctx.wp_d is not None:
-                check(lib.hmvae_conv_dgrad_tc(plan.handle, ptr(gy), ptr(y), ptr(ctx.wp_d), ptr(gxin), b, t_in, stream()), "conv_dgrad_tc")
+                ws = _workspace(plan, b, t_in, 1, x.device)
+                check(lib.hmvae_conv_dgrad_tc(plan.handle, ptr(gy), ptr(y), ptr(ctx.wp_d), ptr(gxin), b, t_in, ptr(ws), ws.numel() * 4,
+                                              stream()), "conv_dgrad_tc")
             else:
                 check(lib.hmvae_conv_dgrad(plan.handle, ptr(gy), ptr(y), ptr(w), ptr(gxin), b, t_in, _conv_impl, stream()), "conv_dgrad")
             if plan.has_prologue:

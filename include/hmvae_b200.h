@@ -83,10 +83,14 @@ int hmvae_conv_wgrad(const hmvae_conv_plan* plan, const float* x, const float* d
 int hmvae_conv_tc_supported(const hmvae_conv_plan* plan, int batch, int t_in, int mode);
 int hmvae_conv_packed_size(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad);   /* floats */
 int hmvae_conv_pack_weights(const hmvae_conv_plan* plan, const float* w, float* wp_fprop, float* wp_dgrad, void* stream);
+/* workspace: device scratch for the staged (padded / upsampled / tf32-rounded) activation tiles, at least
+ * hmvae_conv_tc_workspace(plan, batch, t_in, mode) bytes, 16-byte aligned; contents are dead after the call returns
+ * (stream-ordered). */
+long hmvae_conv_tc_workspace(const hmvae_conv_plan* plan, int batch, int t_in, int mode);
 int hmvae_conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float* wp_fprop, const float* bias, float* y,
-                        int batch, int t_in, void* stream);
+                        int batch, int t_in, void* workspace, long workspace_bytes, void* stream);
 int hmvae_conv_dgrad_tc(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* wp_dgrad, float* dxin,
-                        int batch, int t_in, void* stream);
+                        int batch, int t_in, void* workspace, long workspace_bytes, void* stream);
 
 /* adjoint of the prologue: dsrc[B, src_joints*ci, T_src] from dxin[B, J*ci, T]; if src_act != NULL the result is
  * multiplied by lrelu'(src_act) (src_act = the activation tensor that fed this layer). */

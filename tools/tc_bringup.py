@@ -60,6 +60,18 @@ def run_case(name):
     rel = lambda a, r: float((a - r).norm() / r.norm())
     res["y"] = rel(outs[ops.IMPL_TC][0], outs[ops.IMPL_SIMT][0])
     res["dx"] = rel(outs[ops.IMPL_TC][1], outs[ops.IMPL_SIMT][1])
+    # same comparison without the LeakyReLU epilogue: isolates dgrad from sign flips of y ~ 0 between the two forwards
+    kw2 = dict(kw, lrelu=False)
+    o2 = {}
+    for impl in (ops.IMPL_SIMT, ops.IMPL_TC):
+        ops.set_conv_impl(impl)
+        xi = x.clone().requires_grad_(True)
+        y = conv.fused_forward(xi, **kw2)
+        torch.manual_seed(7)
+        y.backward(torch.randn_like(y))
+        torch.cuda.synchronize()
+        o2[impl] = xi.grad.detach()
+    res["dx_nolrelu"] = rel(o2[ops.IMPL_TC], o2[ops.IMPL_SIMT])
     # timing
     ops.set_conv_impl(ops.IMPL_TC)
     for which in ("tc", "simt"):
@@ -82,13 +94,13 @@ def run_case(name):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in CASES:
-        run_case(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[1] == "--one":
+        run_case(sys.argv[2])
     else:
         names = sys.argv[1:] or list(CASES)
         for n in names:
             try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), n], capture_output=True, text=True, timeout=120)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", n], capture_output=True, text=True, timeout=120)
                 out = (r.stdout.strip().splitlines() or ["(no output)"])[-1]
                 if r.returncode != 0:
                     out += " | rc=%d %s" % (r.returncode, r.stderr.strip().splitlines()[-1] if r.stderr.strip() else "")
