@@ -162,6 +162,19 @@ class KernelTimer:
             d["calls"] += 1
         return out
 
+    def per_layer(self, steps):
+        """conv time per (entry point, layer); layers are labelled by the order their plans first appear in a step."""
+        torch.cuda.synchronize()
+        order, out = {}, {}
+        for name, a, e0, e1 in self.records:
+            if not name.startswith("hmvae_conv_") or name in ("hmvae_conv_tc_supported", "hmvae_conv_tc_workspace", "hmvae_conv_packed_size"):
+                continue
+            key = a[0].value if hasattr(a[0], "value") else a[0]
+            idx = order.setdefault(key, len(order))
+            k = "%s[L%d]" % (name.replace("hmvae_conv_", ""), idx)
+            out[k] = out.get(k, 0.0) + e0.elapsed_time(e1) / steps
+        return {k: round(v * 1e3, 1) for k, v in sorted(out.items())}
+
 
 def conv_flops_per_step(model, batch):
     """Algorithmic FLOPs of the unmasked blocks only: 2*B*T_out*K*co*ci*nnz per conv, fwd; x3 for fwd+bwd."""
@@ -325,7 +338,8 @@ def run_b200(args, hp):
                     "algorithmic_flops_per_launch_set": fl_fwd,
                     "ms_per_step_in_kernel": top_ms,
                     "kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])},
-                    "kernel_ms_total_per_step_eager": total_kernel_ms}
+                    "kernel_ms_total_per_step_eager": total_kernel_ms,
+                    "conv_us_per_layer": kt.per_layer(prof_steps)}
         fk = fk_sweep(dev, pk) if args.fk_sweep else None
         cpu = None
         if args.cpu_baseline:

@@ -45,7 +45,9 @@ extern "C" int hmvae_conv_plan_create(const hmvae_conv_desc* desc, const int* nb
   if (nb_off[0] != 0 || nnz < 0 || nnz > J * J) return fail_arg("conv_plan_create: bad neighbour CSR");
   const int src_J = unpool_src ? d.src_joints : J;
   if (src_J < 1 || src_J > 64) return fail_arg("conv_plan_create: bad src_joints");
+  static std::atomic<unsigned long long> next_uid{1};
   hmvae_conv_plan* p = new hmvae_conv_plan();
+  p->uid = next_uid.fetch_add(1);
   p->d = d;
   p->nb_off.assign(nb_off, nb_off + J + 1);
   p->nb_idx.assign(nb_idx, nb_idx + nnz);
@@ -98,6 +100,7 @@ extern "C" int hmvae_conv_plan_create(const hmvae_conv_desc* desc, const int* nb
 extern "C" void hmvae_conv_plan_destroy(hmvae_conv_plan* plan) {
   if (!plan) return;
   cudaFree(plan->dev_tables);
+  for (auto& kv : plan->tc_tables) cudaFree(kv.second);
   delete plan;
 }
 

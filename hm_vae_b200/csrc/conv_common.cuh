@@ -1,5 +1,6 @@
 // Skeleton-aware conv: plan (immutable index tables) shared by the CUDA-core and the tcgen05 implementations.
 #pragma once
+#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -26,6 +27,8 @@ struct hmvae_conv_plan {
   std::vector<int> nb_off, nb_idx, src;
   int* dev_tables;
   int max_nb;   // largest neighbour-list length
+  unsigned long long uid;   // unique per created plan (keys host-side caches; never reused, unlike the address)
+  mutable std::map<int, void*> tc_tables;   // per (mode, joints-per-CTA) work tables of the tcgen05 kernels (device memory)
 };
 
 namespace hmvae {

@@ -24,6 +24,8 @@
 // 148 SMs (small B*T, big channel counts) are additionally split along the reduction (neighbour joints x channel blocks)
 // over gridDim.z; the partial sums go to a workspace and conv_tc_finish_kernel adds them in a fixed order (deterministic)
 // together with bias / LeakyReLU.
+#include <string.h>
+
 #include "conv_common.cuh"
 
 namespace hmvae {
@@ -49,6 +51,7 @@ struct TcArgs {
   int a_bytes, stage_bytes;
   int tmem_cols;
   int splits, split_len;   // split-K: gridDim.z CTAs per (tile, group), each handles split_len consecutive stages
+  const struct TcWorkG* wtab;   // [groups] host-built work tables (device memory, cached in the plan)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -95,33 +98,55 @@ __device__ __forceinline__ long tc_out_index(const ConvArgs& a, long b, int j, i
 }
 
 // ---------------------------------------------------------------------------------------------- weight packing
-// wp[block][k][q][n_pad][4]:  fprop: block = CSR position (j, n), rows = out channels o, cols = in channels c.
-//                             dgrad: block = transposed-CSR position (n, j), rows = in channels c, cols = out channels o.
-__global__ void conv_pack_kernel(ConvArgs a, const float* __restrict__ w, float* __restrict__ wp, int mode, int n_pad,
-                                 int ck_pad, int KC, long total) {
+// wp[block][cb][k][h][n_pad][4]  (cb = KC-channel block of the reduction channels, h = 16-byte chunk inside it)
+//   fprop: block = CSR position (j, n), rows = out channels o, reduction channels = in channels c.
+//   dgrad: block = transposed-CSR position (n, j), rows = in channels c, reduction channels = out channels o.
+// One CTA reads the contiguous ci*K run(s) of the dense weight for its output channel(s) (coalesced) and scatters 16-byte
+// groups.  Padding rows / channels are never written: the packed buffer is zero-filled once when it is allocated.
+__global__ void __launch_bounds__(128) conv_pack_kernel(ConvArgs a, const float* __restrict__ w, float4* __restrict__ wp,
+                                                        int mode, int n_pad, int ck_pad, int KC) {
+  extern __shared__ float rows[];               // mode 0: [ci*K]   mode 1: [4][ci*K]
   const int Cin = a.J * a.ci;
-  const int per_blk = a.K * ck_pad * n_pad;
-  const int qpb = KC / 4;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int blk = (int)(e / per_blk);
-    int r = (int)(e % per_blk);
-    const int c4 = r & 3; r >>= 2;
-    const int row = r % n_pad; r /= n_pad;
-    const int h = r % qpb; r /= qpb;
-    const int k = r % a.K;
-    const int cb = r / a.K;
-    const int col = (cb * qpb + h) * 4 + c4;
-    float v = 0.f;
-    if (mode == 0) {
-      const int j = a.blk_j[blk], n = a.blk_n[blk];
-      if (row < a.co && col < a.ci) v = w[((long)(j * a.co + row) * Cin + n * a.ci + col) * a.K + k];
-    } else {
-      int n = 0;
-      while (a.nbT_off[n + 1] <= blk) ++n;
-      const int j = a.nbT_idx[blk];
-      if (row < a.ci && col < a.co) v = w[((long)(j * a.co + col) * Cin + n * a.ci + row) * a.K + k];
+  const int run = a.ci * a.K;
+  const int qpb = KC / 4, ncb = ck_pad / KC;
+  if (mode == 0) {
+    const int blk = blockIdx.x / a.co, o = blockIdx.x % a.co;
+    const int j = a.blk_j[blk], n = a.blk_n[blk];
+    const float* src = w + ((long)(j * a.co + o) * Cin + n * a.ci) * a.K;
+    for (int e = threadIdx.x; e < run; e += blockDim.x) rows[e] = src[e];
+    __syncthreads();
+    const int nq = (a.ci + 3) / 4;
+    for (int it = threadIdx.x; it < nq * a.K; it += blockDim.x) {
+      const int k = it % a.K, q = it / a.K;
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (q * 4 + i < a.ci) ? __uint_as_float(to_tf32(rows[(q * 4 + i) * a.K + k])) : 0.f;
+      const int cb = q / qpb, h = q % qpb;
+      wp[((((long)blk * ncb + cb) * a.K + k) * qpb + h) * n_pad + o] = make_float4(v[0], v[1], v[2], v[3]);
     }
-    wp[e] = __uint_as_float(to_tf32(v));
+  } else {
+    const int no4 = (a.co + 3) / 4;
+    const int blk = blockIdx.x / no4, o4 = blockIdx.x % no4;
+    int n = 0;
+    while (a.nbT_off[n + 1] <= blk) ++n;
+    const int j = a.nbT_idx[blk];
+    for (int i = 0; i < 4; ++i) {
+      const int o = o4 * 4 + i;
+      if (o < a.co) {
+        const float* src = w + ((long)(j * a.co + o) * Cin + n * a.ci) * a.K;
+        for (int e = threadIdx.x; e < run; e += blockDim.x) rows[i * run + e] = src[e];
+      } else {
+        for (int e = threadIdx.x; e < run; e += blockDim.x) rows[i * run + e] = 0.f;
+      }
+    }
+    __syncthreads();
+    const int cb = o4 / qpb, h = o4 % qpb;
+    for (int it = threadIdx.x; it < run; it += blockDim.x) {
+      const int k = it % a.K, c = it / a.K;
+      const float4 v = make_float4(__uint_as_float(to_tf32(rows[0 * run + it])), __uint_as_float(to_tf32(rows[1 * run + it])),
+                                   __uint_as_float(to_tf32(rows[2 * run + it])), __uint_as_float(to_tf32(rows[3 * run + it])));
+      wp[((((long)blk * ncb + cb) * a.K + k) * qpb + h) * n_pad + c] = v;
+    }
   }
 }
 
@@ -177,11 +202,15 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(TcArgs p, const float
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
-struct TcWork {
-  unsigned int started;
+// which (local out joint, packed weight block) pairs consume the activation tile of K-side joint n, for one joint group
+struct TcWorkG {
   int cnt[64];
   unsigned char jl[64][TC_MAX_NB];
   int blk[64][TC_MAX_NB];
+};
+struct TcWork {
+  TcWorkG g;
+  unsigned int started;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const unsigned char* __restrict__ astage,
@@ -214,18 +243,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int n = tid; n < a.J; n += TC_THREADS) {
-    int c = 0;
-    for (int jl = 0; jl < gj; ++jl) {
-      const int j = j0 + jl;
-      for (int m = p.off[j]; m < p.off[j + 1]; ++m)
-        if (p.idx[m] == n && c < TC_MAX_NB) {
-          work.jl[n][c] = (unsigned char)jl;
-          work.blk[n][c] = m;
-          ++c;
-        }
-    }
-    work.cnt[n] = c;
+  {
+    const int4* wsrc = reinterpret_cast<const int4*>(p.wtab + blockIdx.y);
+    int4* wdst = reinterpret_cast<int4*>(&work.g);
+    for (int i = tid; i < (int)(sizeof(TcWorkG) / 16); i += TC_THREADS) wdst[i] = wsrc[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -240,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
     int s = 0, si = 0;
     uint32_t ph = 0;
     for (int n = 0; n < a.J; ++n) {
-      const int cnt = work.cnt[n];
+      const int cnt = work.g.cnt[n];
       if (cnt == 0) continue;
       for (int cb = 0; cb < ncb; ++cb, ++si) {
         if (si < si_beg || si >= si_end) continue;
@@ -252,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
         }
         __syncwarp();
         if (lane < cnt) {
-          const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(wp) + ((size_t)work.blk[n][lane] * ncb + cb) * piece;
+          const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(wp) + ((size_t)work.g.blk[n][lane] * ncb + cb) * piece;
           bulk_g2s(st + p.a_bytes + (size_t)lane * piece, gsrc, piece, &full_bar[s]);
         }
         if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -264,7 +285,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
     int s = 0, si = 0;
     uint32_t ph = 0, started = 0;
     for (int n = 0; n < a.J; ++n) {
-      const int cnt = work.cnt[n];
+      const int cnt = work.g.cnt[n];
       if (cnt == 0) continue;
       for (int cb = 0; cb < ncb; ++cb, ++si) {
         if (si < si_beg || si >= si_end) continue;
@@ -273,21 +294,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
         if (lane == 0) {
           const uint32_t a_base = smem_u32(smem_raw + (size_t)s * p.stage_bytes);
           const uint32_t b_base = a_base + p.a_bytes;
+          // descriptors: only the 14-bit start-address field (16-byte units, low word) changes between MMAs
+          const uint64_t adesc0 = tc_desc(a_base, (uint32_t)p.rows_alloc * 16, 128);
+          const uint64_t bdesc0 = tc_desc(b_base, (uint32_t)p.n_pad * 16, 128);
+          const uint32_t a_kk = 2u * (uint32_t)p.rows_alloc, b_kk = 2u * (uint32_t)p.n_pad;   // next 8 channels
+          const uint32_t tap_u = tap_bytes >> 4, piece_u = piece >> 4;
           for (int e = 0; e < cnt; ++e) {
-            const int jl = work.jl[n][e];
+            const int jl = work.g.jl[n][e];
             const uint32_t d_addr = tmem_base + (uint32_t)(jl * p.n_pad);
             uint32_t acc = (started >> jl) & 1u;
+            const uint64_t bdesc_e = bdesc0 + (uint64_t)((uint32_t)e * piece_u);
             for (int k = 0; k < a.K; ++k) {
-              int shift;
-              if (p.mode == 0) shift = (a.s == 1) ? k * p.Bt : ((k & 1) * p.Tp2 + (k >> 1)) * p.Bt;
-              else shift = (a.K - 1 - k) * p.Bt;
-              const uint32_t a_k = a_base + (uint32_t)shift * 16;
-              const uint32_t b_k = b_base + (uint32_t)e * piece + (uint32_t)k * tap_bytes;
+              uint32_t shift;
+              if (p.mode == 0) shift = (a.s == 1) ? (uint32_t)(k * p.Bt) : (uint32_t)(((k & 1) * p.Tp2 + (k >> 1)) * p.Bt);
+              else shift = (uint32_t)((a.K - 1 - k) * p.Bt);
+              uint64_t adesc = adesc0 + shift;
+              uint64_t bdesc = bdesc_e + (uint64_t)((uint32_t)k * tap_u);
               for (int kk = 0; kk < qpb / 2; ++kk) {       // one MMA per 8 reduction channels (2 chunks)
-                const uint64_t adesc = tc_desc(a_k + (uint32_t)kk * 2 * p.rows_alloc * 16, (uint32_t)p.rows_alloc * 16, 128);
-                const uint64_t bdesc = tc_desc(b_k + (uint32_t)kk * 2 * p.n_pad * 16, (uint32_t)p.n_pad * 16, 128);
                 tc_mma_tf32(d_addr, adesc, bdesc, idesc, acc);
                 acc = 1;
+                adesc += a_kk;
+                bdesc += b_kk;
               }
             }
             started |= 1u << jl;
@@ -427,11 +454,28 @@ static inline int rup(int v, int m) { return (v + m - 1) / m * m; }
 static int tc_pick_kc(int ck_pad, int n_pad, int K) {
   const int kcs[4] = {32, 24, 16, 8};
   for (int i = 0; i < 4; ++i)
-    if (ck_pad % kcs[i] == 0 && K * (kcs[i] / 4) * n_pad * 16 <= 32 * 1024) return kcs[i];
+    if (ck_pad % kcs[i] == 0 && K * (kcs[i] / 4) * n_pad * 16 <= 16 * 1024) return kcs[i];
   return 8;
 }
 
+static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out);
+
+// geometry is a pure function of (plan, mode, B, T): memoised, so the per-call host cost is one map lookup
 static bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out) {
+  static thread_local std::map<std::pair<unsigned long long, long>, std::pair<bool, TcArgs>> cache;
+  const auto key = std::make_pair(plan->uid, ((long)mode << 48) | ((long)B << 20) | (long)T);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    TcArgs p;
+    memset(&p, 0, sizeof(p));
+    const bool ok = tc_geometry_build(plan, B, T, mode, &p);
+    it = cache.emplace(key, std::make_pair(ok, p)).first;
+  }
+  if (it->second.first) *out = it->second.second;
+  return it->second.first;
+}
+
+static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out) {
   const ConvArgs& a = plan->a;
   const hmvae_conv_desc& d = plan->d;
   if (a.J > 64) return false;
@@ -519,12 +563,56 @@ static bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcA
       longest = c > longest ? c : longest;
     }
     const int ctas = p.mtiles * ((a.J + p.GJ - 1) / p.GJ);
-    int splits = (2 * 148 + ctas - 1) / ctas;
-    if (splits > longest / 2) splits = longest / 2;       // at least 2 stages per CTA
+    int splits = num_sms() / ctas;                         // fill one wave of SMs, no more (fixed per-CTA cost dominates)
+    if (splits > longest / 3) splits = longest / 3;        // at least 3 stages per CTA
     if (splits < 1) splits = 1;
     if (splits > 64) splits = 64;
     p.split_len = (longest + splits - 1) / splits;
     p.splits = (longest + p.split_len - 1) / p.split_len;
+  }
+  {
+    const int key = mode * 1000 + p.GJ;
+    auto it = plan->tc_tables.find(key);
+    if (it == plan->tc_tables.end()) {
+      const int groups = (a.J + p.GJ - 1) / p.GJ;
+      std::vector<TcWorkG> host(groups);
+      // CSR of the N-side joints (fprop: nb lists; dgrad: transpose), block index = CSR position
+      std::vector<int> off(a.J + 1, 0), idx;
+      if (mode == 0) {
+        off = plan->nb_off;
+        idx = plan->nb_idx;
+      } else {
+        for (int n = 0; n < a.J; ++n) {
+          for (int j = 0; j < a.J; ++j)
+            for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m)
+              if (plan->nb_idx[m] == n) idx.push_back(j);
+          off[n + 1] = (int)idx.size();
+        }
+      }
+      for (int g = 0; g < groups; ++g) {
+        TcWorkG& w = host[g];
+        memset(&w, 0, sizeof(w));
+        for (int jl = 0; jl < p.GJ && g * p.GJ + jl < a.J; ++jl) {
+          const int j = g * p.GJ + jl;
+          for (int m = off[j]; m < off[j + 1]; ++m) {
+            const int n = idx[m];
+            if (w.cnt[n] < TC_MAX_NB) {
+              w.jl[n][w.cnt[n]] = (unsigned char)jl;
+              w.blk[n][w.cnt[n]] = m;
+              w.cnt[n]++;
+            }
+          }
+        }
+      }
+      void* dev = nullptr;
+      if (cudaMalloc(&dev, groups * sizeof(TcWorkG)) != cudaSuccess) return false;
+      if (cudaMemcpy(dev, host.data(), groups * sizeof(TcWorkG), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(dev);
+        return false;
+      }
+      it = plan->tc_tables.emplace(key, dev).first;
+    }
+    p.wtab = reinterpret_cast<const TcWorkG*>(it->second);
   }
   int cols = p.GJ * p.n_pad, pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
@@ -559,20 +647,21 @@ void conv_packed_sizes(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad
 
 int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* wp_d, cudaStream_t st) {
   const ConvArgs& a = plan->a;
-  long nf, nd;
-  conv_packed_sizes(plan, &nf, &nd);
-  const long cap = (long)num_sms() * 16;
   if (wp_f) {
-    long blocks = (nf + 255) / 256;
-    conv_pack_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, w, wp_f, 0, rup(a.co, 16), rup(a.ci, 8),
-                                                                         tc_pick_kc(rup(a.ci, 8), rup(a.co, 16), a.K), nf);
+    const int n_pad = rup(a.co, 16), ck_pad = rup(a.ci, 8);
+    const size_t smem = (size_t)a.ci * a.K * 4;
+    conv_pack_kernel<<<a.nnz * a.co, 128, smem, st>>>(a, w, reinterpret_cast<float4*>(wp_f), 0, n_pad, ck_pad,
+                                                      tc_pick_kc(ck_pad, n_pad, a.K));
     int rc = check_launch("conv_pack(fprop)");
     if (rc) return rc;
   }
   if (wp_d) {
-    long blocks = (nd + 255) / 256;
-    conv_pack_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, w, wp_d, 1, rup(a.ci, 16), rup(a.co, 8),
-                                                                         tc_pick_kc(rup(a.co, 8), rup(a.ci, 16), a.K), nd);
+    const int n_pad = rup(a.ci, 16), ck_pad = rup(a.co, 8);
+    const size_t smem = (size_t)4 * a.ci * a.K * 4;
+    if (smem > 48 * 1024)
+      HMVAE_CUDA(cudaFuncSetAttribute(conv_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_pack_kernel<<<a.nnz * ((a.co + 3) / 4), 128, smem, st>>>(a, w, reinterpret_cast<float4*>(wp_d), 1, n_pad, ck_pad,
+                                                                 tc_pick_kc(ck_pad, n_pad, a.K));
     int rc = check_launch("conv_pack(dgrad)");
     if (rc) return rc;
   }

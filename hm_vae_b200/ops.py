@@ -78,8 +78,8 @@ class PackedWeights:
     def get(self, weight):
         key = (weight._version, weight.data_ptr())
         if self.wp_f is None or self.wp_f.device != weight.device:
-            self.wp_f = torch.empty(self.nf, device=weight.device, dtype=torch.float32)
-            self.wp_d = torch.empty(self.nd, device=weight.device, dtype=torch.float32)
+            self.wp_f = torch.zeros(self.nf, device=weight.device, dtype=torch.float32)   # padding stays zero forever
+            self.wp_d = torch.zeros(self.nd, device=weight.device, dtype=torch.float32)
             self.key = None
         if key != self.key or _force_repack:
             check(lib.hmvae_conv_pack_weights(self.plan.handle, ptr(weight.detach()), ptr(self.wp_f), ptr(self.wp_d), stream()),
