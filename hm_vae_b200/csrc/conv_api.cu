@@ -25,6 +25,10 @@ int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* w
 int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, const float* wp,
                    const float* bias, float* dst, int B, int T, void* workspace, long workspace_bytes, cudaStream_t st);
 long conv_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T, int mode);
+bool conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int B, int T);
+long conv_wgrad_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T);
+int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* yact, float* dw,
+                         float* dbias, int B, int T, int accumulate, void* workspace, long workspace_bytes, cudaStream_t st);
 }  // namespace hmvae
 
 using namespace hmvae;
@@ -192,4 +196,26 @@ extern "C" int hmvae_conv_wgrad(const hmvae_conv_plan* plan, const float* x, con
   if (batch == 0) return 0;
   (void)impl;
   return conv_wgrad_simt(plan, x, dy, y, dw, dbias, batch, t_in, st);
+}
+
+/* mode 2 = wgrad in hmvae_conv_tc_supported / hmvae_conv_tc_workspace is handled by these dedicated entry points */
+extern "C" int hmvae_conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int batch, int t_in) {
+  if (!plan || batch < 1 || t_in < 1) return 0;
+  if (check_shape(plan, batch, t_in, "conv_wgrad_tc_supported")) return 0;
+  return conv_wgrad_tc_supported(plan, batch, t_in) ? 1 : 0;
+}
+
+extern "C" long hmvae_conv_wgrad_tc_workspace(const hmvae_conv_plan* plan, int batch, int t_in) {
+  if (!plan || batch < 1 || t_in < 1) return -1;
+  return conv_wgrad_tc_workspace_bytes(plan, batch, t_in);
+}
+
+extern "C" int hmvae_conv_wgrad_tc(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* y, float* dw,
+                                   float* dbias, int batch, int t_in, int accumulate, void* workspace, long workspace_bytes,
+                                   void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_wgrad_tc");
+  if (rc) return rc;
+  if (!x || !dy || !dw || (plan->d.lrelu && !y)) return fail_arg("conv_wgrad_tc: null pointer");
+  if (batch == 0) return 0;
+  return conv_wgrad_tc_launch(plan, x, dy, y, dw, dbias, batch, t_in, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], accum_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ TcWork work;
+  __shared__ __align__(16) TcWork work;
 
   const ConvArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -294,30 +294,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
         if (lane == 0) {
           const uint32_t a_base = smem_u32(smem_raw + (size_t)s * p.stage_bytes);
           const uint32_t b_base = a_base + p.a_bytes;
-          // descriptors: only the 14-bit start-address field (16-byte units, low word) changes between MMAs
+          // Descriptors: only the 14-bit start-address field (16-byte units, low word) changes between MMAs, and between
+          // consecutive taps it changes by a constant, so the issue loop is two adds + one tcgen05.mma per instruction.
+          //   fprop stride 1: tap k reads rows shifted by k*Bt           -> one run  k = 0..K-1,      a += Bt
+          //   fprop stride 2: even taps read phase 0, odd taps phase 1    -> two runs (k even / odd),  a += Bt, b += 2 taps
+          //   dgrad         : tap k reads rows shifted by (K-1-k)*Bt      -> one run  k = 0..K-1,      a -= Bt
           const uint64_t adesc0 = tc_desc(a_base, (uint32_t)p.rows_alloc * 16, 128);
           const uint64_t bdesc0 = tc_desc(b_base, (uint32_t)p.n_pad * 16, 128);
-          const uint32_t a_kk = 2u * (uint32_t)p.rows_alloc, b_kk = 2u * (uint32_t)p.n_pad;   // next 8 channels
+          const uint64_t a_kk = 2u * (uint32_t)p.rows_alloc, b_kk = 2u * (uint32_t)p.n_pad;   // next 8 reduction channels
           const uint32_t tap_u = tap_bytes >> 4, piece_u = piece >> 4;
+          const int nrun = (p.mode == 0 && a.s == 2) ? 2 : 1;
+          const int nkk = qpb / 2;
           for (int e = 0; e < cnt; ++e) {
             const int jl = work.g.jl[n][e];
             const uint32_t d_addr = tmem_base + (uint32_t)(jl * p.n_pad);
             uint32_t acc = (started >> jl) & 1u;
-            const uint64_t bdesc_e = bdesc0 + (uint64_t)((uint32_t)e * piece_u);
-            for (int k = 0; k < a.K; ++k) {
-              uint32_t shift;
-              if (p.mode == 0) shift = (a.s == 1) ? (uint32_t)(k * p.Bt) : (uint32_t)(((k & 1) * p.Tp2 + (k >> 1)) * p.Bt);
-              else shift = (uint32_t)((a.K - 1 - k) * p.Bt);
-              uint64_t adesc = adesc0 + shift;
-              uint64_t bdesc = bdesc_e + (uint64_t)((uint32_t)k * tap_u);
-              for (int kk = 0; kk < qpb / 2; ++kk) {       // one MMA per 8 reduction channels (2 chunks)
-                tc_mma_tf32(d_addr, adesc, bdesc, idesc, acc);
-                acc = 1;
-                adesc += a_kk;
-                bdesc += b_kk;
+            started |= 1u << jl;
+            for (int run = 0; run < nrun; ++run) {
+              uint64_t ad, bd = bdesc0 + (uint64_t)((uint32_t)e * piece_u + (uint32_t)run * tap_u);
+              long a_step;
+              int ntap;
+              if (p.mode == 1) { ad = adesc0 + (uint32_t)((a.K - 1) * p.Bt); a_step = -(long)p.Bt; ntap = a.K; }
+              else if (nrun == 1) { ad = adesc0; a_step = p.Bt; ntap = a.K; }
+              else { ad = adesc0 + (uint32_t)(run * p.Tp2 * p.Bt); a_step = p.Bt; ntap = (a.K - run + 1) / 2; }
+              const uint64_t b_step = (uint64_t)tap_u * nrun;
+              if (nkk == 1) {
+#pragma unroll 5
+                for (int tp = 0; tp < ntap; ++tp) {
+                  tc_mma_tf32(d_addr, ad, bd, idesc, acc);
+                  acc = 1;
+                  ad += a_step;
+                  bd += b_step;
+                }
+              } else {
+                for (int tp = 0; tp < ntap; ++tp) {
+                  uint64_t ad2 = ad, bd2 = bd;
+#pragma unroll 4
+                  for (int kk = 0; kk < nkk; ++kk) {
+                    tc_mma_tf32(d_addr, ad2, bd2, idesc, acc);
+                    acc = 1;
+                    ad2 += a_kk;
+                    bd2 += b_kk;
+                  }
+                  ad += a_step;
+                  bd += b_step;
+                }
               }
             }
-            started |= 1u << jl;
           }
           tc_commit(&empty_bar[s]);
         }

@@ -1,0 +1,446 @@
+// Skeleton-aware conv, weight gradient on the tensor cores (tcgen05 kind::tf32, accumulators in TMEM).   sm_100a only.
+//
+//     dW[(j,o), (n,c), k] = sum_{b,t}  dy[b, (j,o), t] * xpad[b, (n,c), t*s + k]          for n in nb(j) only
+//
+// GEMM view per tap k:  D_k[M = 128 dy channels, N = channels of input joint n] += A^T B, reduction over positions.
+// Both operands are MN-major views of staged tiles whose ROWS are positions (time-major, sequence-minor) and whose 16-byte
+// row elements are 4 consecutive channels -- the same kind of tile the fprop/dgrad kernels use -- so
+//   * the 128 M-rows are simply 32 consecutive channel chunks of dy (several consecutive output joints),
+//   * tap k is again a start-address shift of the x tile (k*Bt rows; stride-2 layers keep two input phases),
+//   * one tcgen05.mma consumes 8 positions; the accumulators of a whole tap group (L taps x N columns <= 512) stay in TMEM
+//     while the CTA streams over the batch.
+// One CTA owns (M-slab, input joint n, tap group) => every dW element is written by exactly one thread (deterministic,
+// no atomics, masked blocks are never touched).  (M-slab, n) pairs without any neighbour relation are not launched.
+//
+//   conv_wgrad_prep_kernel : stages dy (with LeakyReLU') and the padded/upsampled/unpooled x as tf32 tiles, one contiguous
+//                            piece per (batch tile, CTA operand) so that the main kernel issues two bulk copies per stage.
+//   conv_wgrad_tc_kernel   : warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (TMEM -> global dW).
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace hmvae {
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_MAX_STAGES = 4;
+
+struct WgItem {      // one CTA
+  int slab, n, k0, L;
+  unsigned long long nbmask;    // bit j set <=> (j, n) is an unmasked block
+};
+
+struct WgArgs {
+  ConvArgs a;
+  int B, T, T_out;
+  int ckd;          // dy channels per joint padded to 8   (M side)
+  int n_pad;        // x channels per joint padded to 16   (N side)
+  int dy_chunks;    // J * ckd / 4
+  int slabs;        // ceil(dy_chunks / 32)
+  int Bt, mtiles;   // sequences per stage
+  int Rd;           // dy rows per stage   = T_out * Bt (multiple of 8)
+  int Rx;           // x rows per phase and stage (window of the tap group)
+  int nphase;       // 1 (stride 1) or 2
+  int TG, Lmax;     // tap groups, taps per group
+  int a_bytes, b_bytes, stage_bytes, stages;
+  int tmem_cols;
+  int nitems;
+  const WgItem* items;
+};
+
+__device__ __forceinline__ uint32_t wg_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ long wg_out_index(const ConvArgs& a, long b, int j, int o, int t, int T_out) {
+  const int ch = j * a.ojs + a.oco + o;
+  const long ctot = (long)a.J * a.ojs;
+  return a.cl ? (b * T_out + t) * ctot + ch : (b * ctot + ch) * T_out + t;
+}
+__device__ __forceinline__ uint64_t wg_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+// tap group geometry: first padded input row (per phase) and number of rows of the window
+__device__ __host__ __forceinline__ void wg_window(int s, int k0, int L, int phase, int* lo, int* cnt) {
+  if (s == 1) { *lo = k0; *cnt = L; return; }
+  // taps k in [k0, k0+L) with k % 2 == phase  ->  shifts k/2
+  int first = k0 + (((k0 & 1) != phase) ? 1 : 0);
+  if (first >= k0 + L) { *lo = 0; *cnt = 0; return; }
+  int last = k0 + L - 1;
+  if ((last & 1) != phase) --last;
+  *lo = first >> 1;
+  *cnt = (last >> 1) - (first >> 1) + 1;
+}
+
+// ---------------------------------------------------------------------------------------------- staging
+// dyw[mt][slab][32][Rd][4]          row = t*Bt + b        (channels beyond the last joint / rows beyond T_out*Bt are zero)
+// xw [mt][n][tg][phase][n_pad/4][Rx][4]   row = (u - lo)*Bt + b,  u = padded input index (stride 1) or index inside the phase
+__global__ void __launch_bounds__(256) conv_wgrad_prep_kernel(WgArgs p, const float* __restrict__ x,
+                                                              const float* __restrict__ dy, const float* __restrict__ yact,
+                                                              float4* __restrict__ dyw, float4* __restrict__ xw) {
+  const ConvArgs& a = p.a;
+  const long n_dy = (long)p.mtiles * p.slabs * 32 * p.Rd;
+  const int nq = p.n_pad / 4;
+  const long n_x = (long)p.mtiles * a.J * p.TG * p.nphase * nq * p.Rx;
+  const int Tq = p.T + 2 * a.p;
+  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < n_dy + n_x; it += (long)gridDim.x * blockDim.x) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (it < n_dy) {
+      const int row = (int)(it % p.Rd);
+      long r = it / p.Rd;
+      const int cq = (int)(r % 32); r /= 32;
+      const int slab = (int)(r % p.slabs);
+      const int mt = (int)(r / p.slabs);
+      const int t = row / p.Bt, b = row % p.Bt;
+      const long bb = (long)mt * p.Bt + b;
+      const int gq = slab * 32 + cq;
+      if (gq < p.dy_chunks && t < p.T_out && bb < p.B) {
+        const int j = gq / (p.ckd / 4), o0 = (gq % (p.ckd / 4)) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (o0 + i < a.co) {
+            const long oi = wg_out_index(a, bb, j, o0 + i, t, p.T_out);
+            float g = dy[oi];
+            if (a.lrelu && !(yact[oi] > 0.f)) g *= 0.2f;
+            v[i] = g;
+          }
+      }
+      dyw[it] = make_float4(__uint_as_float(wg_tf32(v[0])), __uint_as_float(wg_tf32(v[1])), __uint_as_float(wg_tf32(v[2])),
+                            __uint_as_float(wg_tf32(v[3])));
+    } else {
+      const long e = it - n_dy;
+      const int row = (int)(e % p.Rx);
+      long r = e / p.Rx;
+      const int q = (int)(r % nq); r /= nq;
+      const int phase = (int)(r % p.nphase); r /= p.nphase;
+      const int tg = (int)(r % p.TG); r /= p.TG;
+      const int n = (int)(r % a.J);
+      const int mt = (int)(r / a.J);
+      const int k0 = tg * p.Lmax;
+      const int L = (a.K - k0 < p.Lmax) ? a.K - k0 : p.Lmax;
+      int lo, cnt;
+      wg_window(a.s, k0, L, phase, &lo, &cnt);
+      const int u = lo + row / p.Bt, b = row % p.Bt;
+      const long bb = (long)mt * p.Bt + b;
+      const int tp = (a.s == 1) ? u : 2 * u + phase;     // padded input coordinate
+      if (cnt > 0 && row < (p.T_out + cnt - 1) * p.Bt && tp < Tq && bb < p.B) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (q * 4 + i < a.ci) v[i] = load_padded(x, a, bb, n, q * 4 + i, tp, p.T);
+      }
+      xw[e] = make_float4(__uint_as_float(wg_tf32(v[0])), __uint_as_float(wg_tf32(v[1])), __uint_as_float(wg_tf32(v[2])),
+                          __uint_as_float(wg_tf32(v[3])));
+    }
+  }
+}
+
+// db[j*co + o] = sum_{b,t} dy * lrelu'(y)          (one warp per channel)
+__global__ void conv_bias_grad_kernel(ConvArgs a, const float* __restrict__ dy, const float* __restrict__ yact,
+                                      float* __restrict__ db, int B, int T_out, int accumulate) {
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ch >= a.J * a.co) return;
+  const int j = ch / a.co, o = ch % a.co;
+  float acc = 0.f;
+  for (int e = lane; e < B * T_out; e += 32) {
+    const long oi = wg_out_index(a, e / T_out, j, o, e % T_out, T_out);
+    float g = dy[oi];
+    if (a.lrelu && !(yact[oi] > 0.f)) g *= 0.2f;
+    acc += g;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) db[ch] = accumulate ? db[ch] + acc : acc;
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, const unsigned char* __restrict__ dyw,
+                                                                      const unsigned char* __restrict__ xw,
+                                                                      float* __restrict__ dw, int accumulate) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const ConvArgs& a = p.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const WgItem item = p.items[blockIdx.x];
+  const int nq = p.n_pad / 4;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const int tg = item.k0 / p.Lmax;
+
+  if (warp == 0) {
+    // =============================== producer ===============================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int mt = 0; mt < p.mtiles; ++mt) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* st = smem_raw + (size_t)s * p.stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p.a_bytes + p.b_bytes));
+        bulk_g2s(st, dyw + ((size_t)mt * p.slabs + item.slab) * p.a_bytes, (uint32_t)p.a_bytes, &full_bar[s]);
+        bulk_g2s(st + p.a_bytes, xw + (((size_t)mt * a.J + item.n) * p.TG + tg) * p.b_bytes, (uint32_t)p.b_bytes, &full_bar[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    // instruction descriptor: F32 accum, TF32 x TF32, both operands MN-major, N = n_pad, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.n_pad >> 3) << 17) |
+                           ((128u >> 4) << 24);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int mt = 0; mt < p.mtiles; ++mt) {
+      mbar_wait(&full_bar[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_base = smem_u32(smem_raw + (size_t)s * p.stage_bytes);
+        const uint32_t b_base = a_base + p.a_bytes;
+        // MN-major, no swizzle: LBO field = stride between 8-row (K) groups = 128 B, SBO field = stride between 16-byte chunks
+        const uint64_t adesc0 = wg_desc(a_base, 128, (uint32_t)p.Rd * 16);
+        const uint64_t bdesc0 = wg_desc(b_base, 128, (uint32_t)p.Rx * 16);
+        const int ksteps = p.Rd / 8;
+        for (int t = 0; t < item.L; ++t) {
+          const int k = item.k0 + t;
+          int lo, cnt, phase = 0, shift;
+          if (a.s == 1) { shift = t; }
+          else { phase = k & 1; wg_window(2, item.k0, item.L, phase, &lo, &cnt); shift = (k >> 1) - lo; }
+          uint64_t ad = adesc0;
+          uint64_t bd = bdesc0 + (uint32_t)((phase * nq * p.Rx) + shift * p.Bt);
+          const uint32_t d_addr = tmem_base + (uint32_t)(t * p.n_pad);
+          uint32_t acc = (mt > 0) ? 1u : 0u;
+#pragma unroll 4
+          for (int ks = 0; ks < ksteps; ++ks) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.ne.b32 p, %4, 0;\n"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+                "}\n" ::"r"(d_addr),
+                "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
+                : "memory");
+            acc = 1;
+            ad += 8;      // 8 rows * 16 B = 128 B
+            bd += 8;
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s]))
+                     : "memory");
+      }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+    if (lane == 0)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&accum_bar)) : "memory");
+    __syncwarp();
+  } else {
+    // =============================== epilogue (warps 2..5): TMEM -> dW ===============================
+    mbar_wait(&accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int lq = warp & 3;
+    const int m = lq * 32 + lane;
+    const int gch = item.slab * 128 + m;                 // dy channel (padded numbering)
+    const int j = gch / p.ckd, o = gch % p.ckd;
+    const bool valid = j < a.J && o < a.co && ((item.nbmask >> j) & 1ull);
+    const int Cin = a.J * a.ci;
+    float* wrow = dw + ((long)(valid ? j * a.co + o : 0) * Cin + item.n * a.ci) * a.K + item.k0;
+    for (int c16 = 0; c16 < p.n_pad; c16 += 16) {
+      for (int t = 0; t < item.L; ++t) {
+        uint32_t r[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * p.n_pad + c16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c16 + i;
+            if (c < a.ci) {
+              float* dst = wrow + (long)c * a.K + t;
+              const float v = __uint_as_float(r[i]);
+              *dst = accumulate ? *dst + v : v;
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static inline int rup(int v, int m) { return (v + m - 1) / m * m; }
+
+static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs* out, std::vector<WgItem>* items_out) {
+  const ConvArgs& a = plan->a;
+  if (a.J > 64 || a.K > 32) return false;
+  WgArgs p;
+  memset(&p, 0, sizeof(p));
+  p.a = a;
+  p.B = B;
+  p.T = T;
+  p.T_out = conv_t_out(plan->d, T);
+  p.ckd = rup(a.co, 8);
+  p.n_pad = rup(a.ci, 16);
+  if (p.n_pad > 256) return false;
+  p.dy_chunks = a.J * p.ckd / 4;
+  p.slabs = (p.dy_chunks + 31) / 32;
+  p.nphase = a.s;
+  // taps per group: L * n_pad accumulator columns <= 512
+  p.Lmax = 512 / p.n_pad;
+  if (p.Lmax > a.K) p.Lmax = a.K;
+  p.TG = (a.K + p.Lmax - 1) / p.Lmax;
+  p.Lmax = (a.K + p.TG - 1) / p.TG;                 // balance the groups
+  int cols = p.Lmax * p.n_pad, pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  if (pow2 > 512) return false;
+  p.tmem_cols = pow2;
+  // sequences per stage: ~64 dy rows
+  if (p.T_out > 128) return false;
+  p.Bt = 64 / p.T_out;
+  if (p.Bt < 1) p.Bt = 1;
+  if (p.Bt > B) p.Bt = B;
+  while ((p.T_out * p.Bt) % 8 != 0) ++p.Bt;          // K steps of 8 rows (extra sequences are zero rows)
+  p.mtiles = (B + p.Bt - 1) / p.Bt;
+  p.Rd = p.T_out * p.Bt;
+  const int win = (a.s == 1) ? p.Lmax : (p.Lmax + 1) / 2 + 1;
+  p.Rx = rup((p.T_out + win - 1) * p.Bt, 8);
+  p.a_bytes = 32 * p.Rd * 16;
+  p.b_bytes = p.nphase * (p.n_pad / 4) * p.Rx * 16;
+  p.stage_bytes = rup(p.a_bytes + p.b_bytes, 128);
+  p.stages = (200 * 1024) / p.stage_bytes;
+  if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+  if (p.stages < 2) return false;
+  if (p.Rd * 16 >= (1 << 18) || p.Rx * 16 >= (1 << 18)) return false;
+  // work items
+  const int jps = 128 / p.ckd;                       // joints per slab (ckd divides 128 only for 8,16,32,64; handle generally below)
+  (void)jps;
+  std::vector<WgItem> items;
+  for (int slab = 0; slab < p.slabs; ++slab) {
+    const int ch0 = slab * 128, ch1 = ch0 + 128;
+    for (int n = 0; n < a.J; ++n) {
+      unsigned long long mask = 0;
+      bool any = false;
+      for (int j = 0; j < a.J; ++j) {
+        bool nb = false;
+        for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m) nb |= plan->nb_idx[m] == n;
+        if (!nb) continue;
+        mask |= 1ull << j;
+        const int c0 = j * p.ckd, c1 = c0 + a.co;    // channel range of joint j in the padded numbering
+        if (c0 < ch1 && c1 > ch0) any = true;
+      }
+      if (!any) continue;
+      for (int tg = 0; tg < p.TG; ++tg) {
+        WgItem it;
+        it.slab = slab; it.n = n; it.k0 = tg * p.Lmax;
+        it.L = (a.K - it.k0 < p.Lmax) ? a.K - it.k0 : p.Lmax;
+        it.nbmask = mask;
+        if (it.L > 0) items.push_back(it);
+      }
+    }
+  }
+  p.nitems = (int)items.size();
+  *out = p;
+  *items_out = items;
+  return p.nitems > 0;
+}
+
+struct WgCached {
+  bool ok;
+  WgArgs p;
+};
+
+static bool wg_geometry(const hmvae_conv_plan* plan, int B, int T, WgArgs* out) {
+  static thread_local std::map<std::pair<unsigned long long, long>, WgCached> cache;
+  const auto key = std::make_pair(plan->uid, ((long)B << 20) | (long)T);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    WgCached c;
+    std::vector<WgItem> items;
+    c.ok = wg_geometry_build(plan, B, T, &c.p, &items);
+    if (c.ok) {
+      const int tkey = 900000 + (int)(cache.size() % 1000) * 64 + (int)(plan->tc_tables.size());
+      void* dev = nullptr;
+      if (cudaMalloc(&dev, items.size() * sizeof(WgItem)) != cudaSuccess ||
+          cudaMemcpy(dev, items.data(), items.size() * sizeof(WgItem), cudaMemcpyHostToDevice) != cudaSuccess) {
+        c.ok = false;
+      } else {
+        int k2 = tkey;
+        while (plan->tc_tables.count(k2)) ++k2;
+        plan->tc_tables[k2] = dev;                  // freed with the plan
+        c.p.items = reinterpret_cast<const WgItem*>(dev);
+      }
+    }
+    it = cache.emplace(key, c).first;
+  }
+  if (it->second.ok) *out = it->second.p;
+  return it->second.ok;
+}
+
+static long wg_dy_bytes(const WgArgs& p) { return (long)p.mtiles * p.slabs * p.a_bytes; }
+static long wg_x_bytes(const WgArgs& p) { return (long)p.mtiles * p.a.J * p.TG * p.b_bytes; }
+
+bool conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int B, int T) {
+  WgArgs p;
+  return wg_geometry(plan, B, T, &p);
+}
+
+long conv_wgrad_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T) {
+  WgArgs p;
+  if (!wg_geometry(plan, B, T, &p)) return -1;
+  return wg_dy_bytes(p) + wg_x_bytes(p);
+}
+
+int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* yact, float* dw,
+                         float* dbias, int B, int T, int accumulate, void* workspace, long workspace_bytes,
+                         cudaStream_t st) {
+  WgArgs p;
+  if (!wg_geometry(plan, B, T, &p)) return fail_arg("conv_wgrad (tcgen05): unsupported geometry");
+  if (!workspace || workspace_bytes < wg_dy_bytes(p) + wg_x_bytes(p) || !aligned16(workspace))
+    return fail_arg("conv_wgrad (tcgen05): workspace too small or misaligned");
+  unsigned char* dyw = reinterpret_cast<unsigned char*>(workspace);
+  unsigned char* xw = dyw + wg_dy_bytes(p);
+  {
+    const long items = (wg_dy_bytes(p) + wg_x_bytes(p)) / 16;
+    long blocks = (items + 255) / 256, cap = (long)num_sms() * 8;
+    conv_wgrad_prep_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, x, dy, yact, reinterpret_cast<float4*>(dyw),
+                                                                             reinterpret_cast<float4*>(xw));
+    int rc = check_launch("conv_wgrad_prep");
+    if (rc) return rc;
+  }
+  if (dbias) {
+    const int ch = p.a.J * p.a.co;
+    conv_bias_grad_kernel<<<(ch + 3) / 4, 128, 0, st>>>(p.a, dy, yact, dbias, B, p.T_out, accumulate);
+    int rc = check_launch("conv_bias_grad");
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  HMVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_wgrad_tc_kernel<<<p.nitems, WG_THREADS, smem, st>>>(p, dyw, xw, dw, accumulate);
+  return check_launch("conv_wgrad_tc");
+}
+
+}  // namespace hmvae

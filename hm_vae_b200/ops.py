@@ -62,6 +62,7 @@ class ConvPlan:
 
 
 _force_repack = False
+_wgrad_tc = True          # tensor-core weight gradient where the geometry is supported (False: CUDA-core wgrad)
 
 
 class PackedWeights:
@@ -154,10 +155,17 @@ class _SkeletonConvFn(Function):
             else:
                 gx = gxin
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw = torch.empty_like(w)
             gb = torch.empty(plan.joints * plan.co, device=x.device, dtype=torch.float32) if ctx.has_bias else None
-            check(lib.hmvae_conv_wgrad(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, _conv_impl, stream()),
-                  "conv_wgrad")
+            if _wgrad_tc and _conv_impl != IMPL_SIMT and lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in):
+                gw = torch.zeros_like(w)                  # masked blocks are never written: they must read 0
+                n = int(lib.hmvae_conv_wgrad_tc_workspace(plan.handle, b, t_in))
+                ws = torch.empty((n + 3) // 4, device=x.device, dtype=torch.float32)
+                check(lib.hmvae_conv_wgrad_tc(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, ptr(ws), ws.numel() * 4,
+                                              stream()), "conv_wgrad_tc")
+            else:
+                gw = torch.empty_like(w)
+                check(lib.hmvae_conv_wgrad(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, _conv_impl, stream()),
+                      "conv_wgrad")
         return gx, gw, gb, None
 
 

@@ -92,6 +92,13 @@ int hmvae_conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float
 int hmvae_conv_dgrad_tc(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* wp_dgrad, float* dxin,
                         int batch, int t_in, void* workspace, long workspace_bytes, void* stream);
 
+/* Weight gradient on the tensor cores.  Only unmasked blocks of dw are written (deterministically, one writer per element);
+ * masked entries keep their previous value, which must be 0.  accumulate != 0 adds into dw / dbias. */
+int hmvae_conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int batch, int t_in);
+long hmvae_conv_wgrad_tc_workspace(const hmvae_conv_plan* plan, int batch, int t_in);
+int hmvae_conv_wgrad_tc(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* y, float* dw, float* dbias,
+                        int batch, int t_in, int accumulate, void* workspace, long workspace_bytes, void* stream);
+
 /* adjoint of the prologue: dsrc[B, src_joints*ci, T_src] from dxin[B, J*ci, T]; if src_act != NULL the result is
  * multiplied by lrelu'(src_act) (src_act = the activation tensor that fed this layer). */
 int hmvae_conv_prologue_bwd(const hmvae_conv_plan* plan, const float* dxin, const float* src_act, float* dsrc,

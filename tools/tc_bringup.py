@@ -66,12 +66,16 @@ def run_case(name):
     for impl in (ops.IMPL_SIMT, ops.IMPL_TC):
         ops.set_conv_impl(impl)
         xi = x.clone().requires_grad_(True)
+        conv.zero_grad()
         y = conv.fused_forward(xi, **kw2)
         torch.manual_seed(7)
         y.backward(torch.randn_like(y))
         torch.cuda.synchronize()
-        o2[impl] = xi.grad.detach()
-    res["dx_nolrelu"] = rel(o2[ops.IMPL_TC], o2[ops.IMPL_SIMT])
+        o2[impl] = (xi.grad.detach(), conv.weight.grad.detach().clone(), conv.bias.grad.detach().clone())
+    res["dx_nolrelu"] = rel(o2[ops.IMPL_TC][0], o2[ops.IMPL_SIMT][0])
+    res["dw_nolrelu"] = rel(o2[ops.IMPL_TC][1], o2[ops.IMPL_SIMT][1])
+    res["db_nolrelu"] = rel(o2[ops.IMPL_TC][2], o2[ops.IMPL_SIMT][2])
+    res["dw_masked_zero"] = float((o2[ops.IMPL_TC][1] * (1 - conv.mask)).abs().sum()) == 0.0
     # timing
     ops.set_conv_impl(ops.IMPL_TC)
     for which in ("tc", "simt"):
