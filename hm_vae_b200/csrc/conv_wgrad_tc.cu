@@ -3,12 +3,13 @@
 //     dW[(j,o), (n,c), k] = sum_{b,t}  dy[b, (j,o), t] * xpad[b, (n,c), t*s + k]          for n in nb(j) only
 //
 // GEMM view per tap k:  D_k[M = 128 dy channels, N = channels of input joint n] += A^T B, reduction over positions.
-// Both operands are MN-major views of staged tiles whose ROWS are positions (time-major, sequence-minor) and whose 16-byte
-// row elements are 4 consecutive channels -- the same kind of tile the fprop/dgrad kernels use -- so
-//   * the 128 M-rows are simply 32 consecutive channel chunks of dy (several consecutive output joints),
-//   * tap k is again a start-address shift of the x tile (k*Bt rows; stride-2 layers keep two input phases),
+// Both operands are K-major tiles (tools/umma_probe: MN-major tf32 operands in the no-swizzle layout return zeros on sm_100a):
+// rows are channels, the reduction index is the position p = t*Bt + b (time-major, sequence-minor, Bt % 4 == 0) and one
+// 16-byte element holds 4 consecutive sequences of the same time step, so
+//   * the 128 M-rows are 128 consecutive dy channels (several consecutive output joints),
+//   * tap k is a start-address shift of the x tile by k*Bt/4 K-chunks (stride-2 layers keep two input phases),
 //   * one tcgen05.mma consumes 8 positions; the accumulators of a whole tap group (L taps x N columns <= 512) stay in TMEM
-//     while the CTA streams over the batch.
+//     while the CTA streams over (batch group, time window) stages.
 // One CTA owns (M-slab, input joint n, tap group) => every dW element is written by exactly one thread (deterministic,
 // no atomics, masked blocks are never touched).  (M-slab, n) pairs without any neighbour relation are not launched.
 //
@@ -36,9 +37,10 @@ struct WgArgs {
   int n_pad;        // x channels per joint padded to 16   (N side)
   int dy_chunks;    // J * ckd / 4
   int slabs;        // ceil(dy_chunks / 32)
-  int Bt, mtiles;   // sequences per stage
-  int Rd;           // dy rows per stage   = T_out * Bt (multiple of 8)
-  int Rx;           // x rows per phase and stage (window of the tap group)
+  int Bt, mtiles;   // sequences per stage (multiple of 4), number of batch groups
+  int Tw, nwin;     // output time steps per stage, windows per sequence
+  int Rd;           // dy positions per stage = Tw * Bt (multiple of 8)
+  int Rx;           // x positions per phase and stage (window of the tap group) = (Tw + win - 1) * Bt
   int nphase;       // 1 (stride 1) or 2
   int TG, Lmax;     // tap groups, taps per group
   int a_bytes, b_bytes, stage_bytes, stages;
@@ -74,63 +76,74 @@ __device__ __host__ __forceinline__ void wg_window(int s, int k0, int L, int pha
 }
 
 // ---------------------------------------------------------------------------------------------- staging
-// dyw[mt][slab][32][Rd][4]          row = t*Bt + b        (channels beyond the last joint / rows beyond T_out*Bt are zero)
-// xw [mt][n][tg][phase][n_pad/4][Rx][4]   row = (u - lo)*Bt + b,  u = padded input index (stride 1) or index inside the phase
+// stage st = mt * nwin + w  (batch group mt, time window w).  Position inside a stage: p = tl*Bt + b.
+// dyw[st][slab][Rd/4][128 rows][4]            rows = dy channels of the slab (padded numbering j*ckd + o)
+// xw [st][n][tg][phase][Rx/4][n_pad rows][4]  rows = channels of input joint n; tl counts from the window's first input index
 __global__ void __launch_bounds__(256) conv_wgrad_prep_kernel(WgArgs p, const float* __restrict__ x,
                                                               const float* __restrict__ dy, const float* __restrict__ yact,
                                                               float4* __restrict__ dyw, float4* __restrict__ xw) {
   const ConvArgs& a = p.a;
-  const long n_dy = (long)p.mtiles * p.slabs * 32 * p.Rd;
-  const int nq = p.n_pad / 4;
-  const long n_x = (long)p.mtiles * a.J * p.TG * p.nphase * nq * p.Rx;
+  const int nst = p.mtiles * p.nwin;
+  const long n_dy = (long)nst * p.slabs * (p.Rd / 4) * 128;
+  const long n_x = (long)nst * a.J * p.TG * p.nphase * (p.Rx / 4) * p.n_pad;
   const int Tq = p.T + 2 * a.p;
+  const int bq = p.Bt / 4;
   for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < n_dy + n_x; it += (long)gridDim.x * blockDim.x) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (it < n_dy) {
-      const int row = (int)(it % p.Rd);
-      long r = it / p.Rd;
-      const int cq = (int)(r % 32); r /= 32;
+      // thread order: time fastest inside (row, b-quad) so that the 4 scalar loads of neighbouring threads coalesce along t
+      long r = it;
+      const int tl = (int)(r % p.Tw); r /= p.Tw;
+      const int b4 = (int)(r % bq); r /= bq;
+      const int row = (int)(r % 128); r /= 128;
       const int slab = (int)(r % p.slabs);
-      const int mt = (int)(r / p.slabs);
-      const int t = row / p.Bt, b = row % p.Bt;
-      const long bb = (long)mt * p.Bt + b;
-      const int gq = slab * 32 + cq;
-      if (gq < p.dy_chunks && t < p.T_out && bb < p.B) {
-        const int j = gq / (p.ckd / 4), o0 = (gq % (p.ckd / 4)) * 4;
+      const int st = (int)(r / p.slabs);
+      const int mt = st / p.nwin, w = st % p.nwin;
+      const int t = w * p.Tw + tl;
+      const int gch = slab * 128 + row;
+      const int j = gch / p.ckd, o = gch % p.ckd;
+      if (j < a.J && o < a.co && t < p.T_out) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (o0 + i < a.co) {
-            const long oi = wg_out_index(a, bb, j, o0 + i, t, p.T_out);
+        for (int i = 0; i < 4; ++i) {
+          const long bb = (long)mt * p.Bt + b4 * 4 + i;
+          if (bb < p.B) {
+            const long oi = wg_out_index(a, bb, j, o, t, p.T_out);
             float g = dy[oi];
             if (a.lrelu && !(yact[oi] > 0.f)) g *= 0.2f;
             v[i] = g;
           }
+        }
       }
-      dyw[it] = make_float4(__uint_as_float(wg_tf32(v[0])), __uint_as_float(wg_tf32(v[1])), __uint_as_float(wg_tf32(v[2])),
-                            __uint_as_float(wg_tf32(v[3])));
+      const long dst = (((long)st * p.slabs + slab) * (p.Rd / 4) + (tl * bq + b4)) * 128 + row;
+      dyw[dst] = make_float4(__uint_as_float(wg_tf32(v[0])), __uint_as_float(wg_tf32(v[1])), __uint_as_float(wg_tf32(v[2])),
+                             __uint_as_float(wg_tf32(v[3])));
     } else {
-      const long e = it - n_dy;
-      const int row = (int)(e % p.Rx);
-      long r = e / p.Rx;
-      const int q = (int)(r % nq); r /= nq;
+      long r = it - n_dy;
+      const int ulmax = p.Rx / p.Bt;
+      const int ul = (int)(r % ulmax); r /= ulmax;
+      const int b4 = (int)(r % bq); r /= bq;
+      const int c = (int)(r % p.n_pad); r /= p.n_pad;
       const int phase = (int)(r % p.nphase); r /= p.nphase;
       const int tg = (int)(r % p.TG); r /= p.TG;
       const int n = (int)(r % a.J);
-      const int mt = (int)(r / a.J);
+      const int st = (int)(r / a.J);
+      const int mt = st / p.nwin, w = st % p.nwin;
       const int k0 = tg * p.Lmax;
       const int L = (a.K - k0 < p.Lmax) ? a.K - k0 : p.Lmax;
       int lo, cnt;
       wg_window(a.s, k0, L, phase, &lo, &cnt);
-      const int u = lo + row / p.Bt, b = row % p.Bt;
-      const long bb = (long)mt * p.Bt + b;
-      const int tp = (a.s == 1) ? u : 2 * u + phase;     // padded input coordinate
-      if (cnt > 0 && row < (p.T_out + cnt - 1) * p.Bt && tp < Tq && bb < p.B) {
+      const int u = w * p.Tw + lo + ul;                   // input index (stride 1: padded coordinate; stride 2: index in phase)
+      const int tp = (a.s == 1) ? u : 2 * u + phase;
+      if (cnt > 0 && ul < p.Tw + cnt - 1 && tp < Tq && c < a.ci) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (q * 4 + i < a.ci) v[i] = load_padded(x, a, bb, n, q * 4 + i, tp, p.T);
+        for (int i = 0; i < 4; ++i) {
+          const long bb = (long)mt * p.Bt + b4 * 4 + i;
+          if (bb < p.B) v[i] = load_padded(x, a, bb, n, c, tp, p.T);
+        }
       }
-      xw[e] = make_float4(__uint_as_float(wg_tf32(v[0])), __uint_as_float(wg_tf32(v[1])), __uint_as_float(wg_tf32(v[2])),
-                          __uint_as_float(wg_tf32(v[3])));
+      const long dst = (((((long)st * a.J + n) * p.TG + tg) * p.nphase + phase) * (p.Rx / 4) + (ul * bq + b4)) * p.n_pad + c;
+      xw[dst] = make_float4(__uint_as_float(wg_tf32(v[0])), __uint_as_float(wg_tf32(v[1])), __uint_as_float(wg_tf32(v[2])),
+                            __uint_as_float(wg_tf32(v[3])));
     }
   }
 }
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int mt = 0; mt < p.mtiles; ++mt) {
+      for (int mt = 0; mt < p.mtiles * p.nwin; ++mt) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* st = smem_raw + (size_t)s * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p.a_bytes + p.b_bytes));
@@ -201,28 +214,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    // instruction descriptor: F32 accum, TF32 x TF32, both operands MN-major, N = n_pad, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.n_pad >> 3) << 17) |
-                           ((128u >> 4) << 24);
+    // instruction descriptor: F32 accum, TF32 x TF32, both operands K-major, N = n_pad, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
     int s = 0;
     uint32_t ph = 0;
-    for (int mt = 0; mt < p.mtiles; ++mt) {
+    for (int mt = 0; mt < p.mtiles * p.nwin; ++mt) {
       mbar_wait(&full_bar[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t a_base = smem_u32(smem_raw + (size_t)s * p.stage_bytes);
         const uint32_t b_base = a_base + p.a_bytes;
-        // MN-major, no swizzle: LBO field = stride between 8-row (K) groups = 128 B, SBO field = stride between 16-byte chunks
-        const uint64_t adesc0 = wg_desc(a_base, 128, (uint32_t)p.Rd * 16);
-        const uint64_t bdesc0 = wg_desc(b_base, 128, (uint32_t)p.Rx * 16);
+        // K-major, no swizzle: LBO = stride between 16-byte K chunks (= rows*16), SBO = stride between 8-row groups (128 B)
+        const uint64_t adesc0 = wg_desc(a_base, 128 * 16, 128);
+        const uint64_t bdesc0 = wg_desc(b_base, (uint32_t)p.n_pad * 16, 128);
         const int ksteps = p.Rd / 8;
+        const uint32_t bq = (uint32_t)p.Bt / 4;
         for (int t = 0; t < item.L; ++t) {
           const int k = item.k0 + t;
           int lo, cnt, phase = 0, shift;
           if (a.s == 1) { shift = t; }
           else { phase = k & 1; wg_window(2, item.k0, item.L, phase, &lo, &cnt); shift = (k >> 1) - lo; }
           uint64_t ad = adesc0;
-          uint64_t bd = bdesc0 + (uint32_t)((phase * nq * p.Rx) + shift * p.Bt);
+          uint64_t bd = bdesc0 + (uint32_t)(phase * (p.Rx / 4) + shift * bq) * (uint32_t)p.n_pad;
           const uint32_t d_addr = tmem_base + (uint32_t)(t * p.n_pad);
           uint32_t acc = (mt > 0) ? 1u : 0u;
 #pragma unroll 4
@@ -236,8 +249,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
                 "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
                 : "memory");
             acc = 1;
-            ad += 8;      // 8 rows * 16 B = 128 B
-            bd += 8;
+            ad += 2 * 128;                     // 8 positions = 2 K-chunks of 128 rows x 16 B (16-byte units)
+            bd += 2 * (uint32_t)p.n_pad;
           }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s]))
@@ -318,18 +331,18 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
   while (pow2 < cols) pow2 <<= 1;
   if (pow2 > 512) return false;
   p.tmem_cols = pow2;
-  // sequences per stage: ~64 dy rows
-  if (p.T_out > 128) return false;
-  p.Bt = 64 / p.T_out;
-  if (p.Bt < 1) p.Bt = 1;
-  if (p.Bt > B) p.Bt = B;
-  while ((p.T_out * p.Bt) % 8 != 0) ++p.Bt;          // K steps of 8 rows (extra sequences are zero rows)
+  // a stage = Bt sequences (multiple of 4) x Tw output time steps, ~64 positions
+  p.Tw = p.T_out < 16 ? p.T_out : 16;
+  p.nwin = (p.T_out + p.Tw - 1) / p.Tw;
+  p.Bt = rup(64 / p.Tw > 4 ? 64 / p.Tw : 4, 4);
+  if (p.Bt > rup(B, 4)) p.Bt = rup(B, 4);
+  while ((p.Tw * p.Bt) % 8 != 0) p.Bt += 4;           // K steps of 8 positions (extra sequences are zero columns)
   p.mtiles = (B + p.Bt - 1) / p.Bt;
-  p.Rd = p.T_out * p.Bt;
+  p.Rd = p.Tw * p.Bt;
   const int win = (a.s == 1) ? p.Lmax : (p.Lmax + 1) / 2 + 1;
-  p.Rx = rup((p.T_out + win - 1) * p.Bt, 8);
-  p.a_bytes = 32 * p.Rd * 16;
-  p.b_bytes = p.nphase * (p.n_pad / 4) * p.Rx * 16;
+  p.Rx = (p.Tw + win - 1) * p.Bt;
+  p.a_bytes = (p.Rd / 4) * 128 * 16;
+  p.b_bytes = p.nphase * (p.Rx / 4) * p.n_pad * 16;
   p.stage_bytes = rup(p.a_bytes + p.b_bytes, 128);
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
@@ -400,8 +413,8 @@ static bool wg_geometry(const hmvae_conv_plan* plan, int B, int T, WgArgs* out) 
   return it->second.ok;
 }
 
-static long wg_dy_bytes(const WgArgs& p) { return (long)p.mtiles * p.slabs * p.a_bytes; }
-static long wg_x_bytes(const WgArgs& p) { return (long)p.mtiles * p.a.J * p.TG * p.b_bytes; }
+static long wg_dy_bytes(const WgArgs& p) { return (long)p.mtiles * p.nwin * p.slabs * p.a_bytes; }
+static long wg_x_bytes(const WgArgs& p) { return (long)p.mtiles * p.nwin * p.a.J * p.TG * p.b_bytes; }
 
 bool conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int B, int T) {
   WgArgs p;
