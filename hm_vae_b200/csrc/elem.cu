@@ -184,6 +184,25 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dist, const float* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------ loss finalize
+// out[i] = acc[i] * scale[i] for i < n; out[n] = sum_i w[i] * out[i]; out[n+1] = sum_i wk[i] * out[i]; then acc is zeroed
+// (ready for the next step).  n <= 8.
+struct LossCoef { float scale[8], w[8], wk[8]; int n; };
+__global__ void loss_finalize_kernel(float* __restrict__ acc, float* __restrict__ out, LossCoef c) {
+  if (threadIdx.x == 0) {
+    float total = 0.f, kl = 0.f;
+    for (int i = 0; i < c.n; ++i) {
+      const float v = acc[i] * c.scale[i];
+      out[i] = v;
+      total += c.w[i] * v;
+      kl += c.wk[i] * v;
+      acc[i] = 0.f;
+    }
+    out[c.n] = total;
+    out[c.n + 1] = kl;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ MSE
 __global__ void __launch_bounds__(EW_TPB) mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                          float* __restrict__ out, long n) {
@@ -427,6 +446,16 @@ extern "C" int hmvae_latent_bwd(const float* dist, const float* eps, const float
   latent_bwd_kernel<<<ew_grid(rows * d), EW_TPB, 0, (cudaStream_t)stream>>>(dist, eps, dz, dkl, ddist, rows, d, kl_scale);
   return check_launch("latent_bwd");
 }
+extern "C" int hmvae_loss_finalize(float* acc, float* out, const float* scale, const float* w, const float* wk, int n,
+                                   void* stream) {
+  if (!acc || !out || !scale || !w || !wk || n < 1 || n > 8) return fail_arg("loss_finalize: bad arguments");
+  LossCoef c;
+  for (int i = 0; i < 8; ++i) { c.scale[i] = i < n ? scale[i] : 0.f; c.w[i] = i < n ? w[i] : 0.f; c.wk[i] = i < n ? wk[i] : 0.f; }
+  c.n = n;
+  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, out, c);
+  return check_launch("loss_finalize");
+}
+
 extern "C" int hmvae_mse_fwd(const float* a, const float* b, float* out, long n, void* stream) {
   if (!a || !b || !out) return fail_arg("mse_fwd: null pointer");
   if (n <= 0) return 0;

@@ -390,6 +390,39 @@ class _LatentFn(Function):
         return gd, None, None
 
 
+class _LatentFusedFn(Function):
+    """z = eps*exp(lv/2)+mu; the KL row-sum is ACCUMULATED into ``kl_acc`` (a 1-element view of a persistent device buffer)
+    and its gradient (weight ``kl_grad_scale`` = kl_w / rows, a host constant) is folded into this op's backward."""
+
+    @staticmethod
+    def forward(ctx, dist, eps, d, kl_grad_scale, kl_acc):
+        dist = dist.contiguous()
+        rows = dist.numel() // (2 * d)
+        z = torch.empty((rows, d), device=dist.device, dtype=torch.float32)
+        check(lib.hmvae_latent_fwd(ptr(dist), ptr(eps), ptr(z), kl_acc.data_ptr(), rows, d, stream()), "latent_fwd")
+        ctx.d, ctx.rows, ctx.scale = d, rows, float(kl_grad_scale)
+        ctx.save_for_backward(dist, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        dist, eps = ctx.saved_tensors
+        gd = torch.empty_like(dist)
+        check(lib.hmvae_latent_bwd(ptr(dist), ptr(eps), ptr(gz.contiguous()), None, ptr(gd), ctx.rows, ctx.d, ctx.scale, stream()),
+              "latent_bwd")
+        return gd, None, None, None, None
+
+
+def latent_fused(dist, eps, d, kl_grad_scale, kl_acc):
+    return _LatentFusedFn.apply(dist, eps, d, kl_grad_scale, kl_acc)
+
+
+def loss_finalize(acc, out, scale, w, wk):
+    n = len(scale)
+    arr = lambda v: (ctypes.c_float * n)(*[float(x) for x in v])
+    check(lib.hmvae_loss_finalize(ptr(acc), ptr(out), arr(scale), arr(w), arr(wk), n, stream()), "loss_finalize")
+
+
 def latent_sample_kl(dist, eps, d):
     """Returns (z [rows, d], kl_sum scalar).  kl mean = kl_sum / rows."""
     return _LatentFn.apply(dist, eps, d)

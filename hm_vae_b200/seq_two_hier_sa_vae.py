@@ -232,6 +232,12 @@ class TwoHierSAVAEModel(nn.Module):
             self._const[key] = t
         return t
 
+    def _loss_buffers(self, device):
+        key = ("loss", str(device))
+        if key not in self._const:
+            self._const[key] = (torch.zeros(8, device=device, dtype=torch.float32), torch.zeros(8, device=device, dtype=torch.float32))
+        return self._const[key]
+
     def _draw_eps(self, z_vec_shapes, device, eps_list):
         """Four randn draws in level order (shapes [B*k_edges, d]) -- the reference's RNG consumption order
         (seq_two_hier_sa_vae.py:419-423).  ``eps_list`` injects them instead (parity tests)."""
@@ -259,44 +265,41 @@ class TwoHierSAVAEModel(nn.Module):
         lat = [self.shallow_latent_d] + [self.latent_d] * (n - 1)
         eps = self._draw_eps([(bs * k_edges[i], lat[i]) for i in range(n)], dev, eps_list) if hp['kl_w'] != 0 else [None] * n
 
-        z_list, kl_sums = [None] * n, [None] * n
-        for zi in (0, n - 1):
+        # persistent accumulators: [sum sq 6d, sum sq rot, sum sq pos, unused, KL sum shallow, KL sum deep]; zeroed by finalize
+        acc, res = self._loss_buffers(dev)
+        z_list = [None] * n
+        levels = (0, n - 1) if n > 1 else (0,)
+        for zi in levels:
             dist = z_vec_list[zi]
-            if zi == 0 and n > 1 and detach_shallow:
+            deep = zi == n - 1
+            kl_w = hp['kl_w'] if deep else hp['shallow_kl_w']
+            slot = acc[5:6] if deep else acc[4:5]
+            if (not deep) and detach_shallow:
                 with torch.no_grad():
-                    z, kl = ops.latent_sample_kl(dist.detach(), eps[zi], lat[zi])
+                    z = ops.latent_fused(dist.detach(), eps[zi], lat[zi], 0.0, slot)
             else:
-                z, kl = ops.latent_sample_kl(dist, eps[zi], lat[zi])
+                z = ops.latent_fused(dist, eps[zi], lat[zi], kl_w / (bs * k_edges[zi]), slot)
             z_list[zi] = z.view(bs, k_edges[zi], -1)
-            kl_sums[zi] = kl
 
         out = self.dec(z_list)                                      # bs X (24*6) X T
-        sums = torch.zeros(4, device=dev, dtype=torch.float32)
         fk_off = self.fk_layer.positions[0].contiguous()
         dx6 = ops.recon_fwdbwd(out.detach(), True, seq_rot_6d, seq_rot_mat, fk_off, self._parents, hp['rec_6d_w'],
-                               hp['rec_rot_w'], hp['rec_pose_w'], sums, want_grad=not validation_flag)
+                               hp['rec_rot_w'], hp['rec_pose_w'], acc, want_grad=not validation_flag)
         nf = float(bs * timesteps)
         j = self.n_joints
-        l_rec_6d = sums[0] / (nf * 6 * j)
-        l_rec_rot_mat = sums[1] / (nf * 9 * j)
-        l_rec_pose = sums[2] / (nf * 3 * j)
-        l_kl_list = [kl_sums[0].detach() / (bs * k_edges[0])] + [torch.zeros(1, device=dev) for _ in range(max(n - 2, 0))]
-        if n > 1:
-            l_kl_list.append(kl_sums[n - 1].detach() / (bs * k_edges[n - 1]))
-        l_kl = hp['kl_w'] * l_kl_list[n - 1] + hp['shallow_kl_w'] * l_kl_list[0]
-        l_total = hp['rec_6d_w'] * l_rec_6d + hp['rec_rot_w'] * l_rec_rot_mat + hp['rec_pose_w'] * l_rec_pose + l_kl
+        kl_deep_w = hp['kl_w'] if n > 1 else 0.0
+        scale = [1.0 / (nf * 6 * j), 1.0 / (nf * 9 * j), 1.0 / (nf * 3 * j), 0.0, 1.0 / (bs * k_edges[0]), 1.0 / (bs * k_edges[n - 1])]
+        w_all = [hp['rec_6d_w'], hp['rec_rot_w'], hp['rec_pose_w'], 0.0, hp['shallow_kl_w'] if n > 1 else hp['kl_w'], kl_deep_w]
+        w_kl = [0.0, 0.0, 0.0, 0.0, w_all[4], w_all[5]]
+        ops.loss_finalize(acc, res, scale, w_all, w_kl)              # one kernel; res = [l6, lrot, lpos, -, kl0, kl3, total, kl]
+        l_rec_6d, l_rec_rot_mat, l_rec_pose = res[0], res[1], res[2]
+        zero = res[3:4]
+        l_kl_list = [res[4]] + [zero for _ in range(max(n - 2, 0))] + ([res[5]] if n > 1 else [])
+        l_total, l_kl = res[6], res[7]
 
         if not validation_flag:
-            tensors, grads = [out], [dx6]
-            if kl_sums[n - 1].requires_grad:
-                tensors.append(kl_sums[n - 1])
-                grads.append(self._scalar(hp['kl_w'] / (bs * k_edges[n - 1]), dev))
-            if n > 1 and kl_sums[0].requires_grad:
-                tensors.append(kl_sums[0])
-                grads.append(self._scalar(hp['shallow_kl_w'] / (bs * k_edges[0]), dev))
-            torch.autograd.backward(tensors, grads)
+            out.backward(dx6)
 
-        zero = torch.zeros(1, device=dev)
         return l_total, l_kl, l_rec_6d, l_rec_rot_mat, l_rec_pose, zero, zero, zero, zero, l_kl_list
 
     # ------------------------------------------------------------------ reference helpers kept for callers

@@ -98,14 +98,16 @@ class Trainer(nn.Module):
     def _record(self, out, validation):
         names = ["total", "kl", "rec_6d", "rec_rot", "rec_pose", "rec_joint_pos", "rec_root_v", "rec_linear_v", "rec_angular_v"]
         prefix = "loss_val_" if validation else "loss_"
+        # every loss is already a scalar (the reference's torch.mean over DataParallel replicas is the identity here)
+        sc = lambda v: v.reshape(()) if v.numel() == 1 else torch.mean(v)
         for n, v in zip(names, out[:9]):
-            setattr(self, prefix + n, torch.mean(v))
+            setattr(self, prefix + n, sc(v))
         if len(out) > 9:
             for i, v in enumerate(out[9]):
-                setattr(self, "loss_hier_kl_%d" % (i + 1), torch.mean(v))
+                setattr(self, "loss_hier_kl_%d" % (i + 1), sc(v))
         if not self.sync_losses:
-            return tuple(torch.mean(v) for v in out[:9])
-        vals = torch.stack([torch.mean(v).reshape(()) for v in out[:9]]).tolist()      # ONE device->host sync
+            return tuple(sc(v) for v in out[:9])
+        vals = torch.stack([sc(v) for v in out[:9]]).tolist()      # ONE device->host sync
         return tuple(vals)
 
     def gen_update(self, data, hp, iterations, multigpus=False, validation_flag=False):

@@ -159,6 +159,10 @@ int hmvae_recon_fwdbwd(const float* x6_pred, int ncw, const float* gt_6d, const 
                        const float* offsets, const int* parents, int joints, int batch, int t,
                        float s6, float srot, float spos, float* losses, float* dx6, float* pos_pred_out,
                        float* gt_pos_out, void* stream);
+/* Turns the atomically accumulated sums into loss values on the device, without a host sync:
+ * out[i] = acc[i]*scale[i] (i<n), out[n] = sum w[i]*out[i] (total), out[n+1] = sum wk[i]*out[i] (weighted KL); acc is zeroed
+ * for the next step.  scale / w / wk are HOST arrays of n <= 8 floats. */
+int hmvae_loss_finalize(float* acc, float* out, const float* scale, const float* w, const float* wk, int n, void* stream);
 /* sum((a-b)^2) atomically added to out[0]; grad: da = scale*(a-b) */
 int hmvae_mse_fwd(const float* a, const float* b, float* out, long n, void* stream);
 int hmvae_mse_bwd(const float* a, const float* b, float* da, long n, float scale, void* stream);
