@@ -314,15 +314,17 @@ def run_b200(args, hp):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
+    # ---- per-kernel attribution (eager, CUDA events around each C-ABI call, after the timed region).  The steps contain the
+    #      gradient all-reduce, so EVERY rank runs them; only rank 0 reports.
+    prof_steps = 5
+    with KernelTimer(_lib.lib) as kt:
+        saved, trainer._graphs = trainer._graphs, {}
+        for _ in range(prof_steps):
+            trainer.gen_update(data, hp, iters0)
+        trainer._graphs = saved
+    barrier()
     line = None
     if rank == 0:
-        # ---- per-kernel attribution (eager, CUDA events around each C-ABI call, after the timed region)
-        prof_steps = 5
-        with KernelTimer(_lib.lib) as kt:
-            saved, trainer._graphs = trainer._graphs, {}
-            for _ in range(prof_steps):
-                trainer.gen_update(data, hp, iters0)
-            trainer._graphs = saved
         summ = kt.summary()
         conv = {k: summ.get(k, dict(ms=0.0, calls=0)) for k in KernelTimer.CONV}
         fl_fwd = conv_flops_per_step(model, bs)
