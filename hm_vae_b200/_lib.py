@@ -93,6 +93,8 @@ _SIGS = {
     "hmvae_latent_fwd": (c_int, [P, P, P, P, c_long, c_int, P]),
     "hmvae_latent_bwd": (c_int, [P, P, P, P, P, c_long, c_int, c_float, P]),
     "hmvae_recon_fwdbwd": (c_int, [P, c_int, P, P, P, IP, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P]),
+    "hmvae_linear_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
+    "hmvae_linear_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_loss_finalize": (c_int, [P, P, POINTER(c_float), POINTER(c_float), POINTER(c_float), c_int, P]),
     "hmvae_mse_fwd": (c_int, [P, P, P, c_long, P]),
     "hmvae_mse_bwd": (c_int, [P, P, P, c_long, c_float, P]),

@@ -25,6 +25,7 @@ int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* w
 int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, const float* wp,
                    const float* bias, float* dst, int B, int T, void* workspace, long workspace_bytes, cudaStream_t st);
 long conv_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T, int mode);
+void conv_tc_release(const hmvae_conv_plan* plan);
 bool conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int B, int T);
 long conv_wgrad_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T);
 int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* yact, float* dw,
@@ -104,6 +105,7 @@ extern "C" int hmvae_conv_plan_create(const hmvae_conv_desc* desc, const int* nb
 extern "C" void hmvae_conv_plan_destroy(hmvae_conv_plan* plan) {
   if (!plan) return;
   cudaFree(plan->dev_tables);
+  conv_tc_release(plan);
   for (auto& kv : plan->tc_tables) cudaFree(kv.second);
   delete plan;
 }

@@ -38,8 +38,6 @@ constexpr int TC_MAX_NB = 16;
 struct TcArgs {
   ConvArgs a;
   int mode;            // 0 fprop, 1 dgrad
-  const int* off;      // CSR over the N-side joints (fprop: nb_off, dgrad: nbT_off)
-  const int* idx;
   int n_real, n_pad;   // N-side channels per joint (real, padded to 16)
   int ck, ck_pad;      // reduction channels per K-side joint (real, padded to 8)
   int KC;              // reduction channels per pipeline stage (multiple of 8, divides ck_pad)
@@ -51,7 +49,7 @@ struct TcArgs {
   int a_bytes, stage_bytes;
   int tmem_cols;
   int splits, split_len;   // split-K: gridDim.z CTAs per (tile, group), each handles split_len consecutive stages
-  const struct TcWorkG* wtab;   // [groups] host-built work tables (device memory, cached in the plan)
+  const struct TcWorkG* wtab;   // [groups] host-built work tables (device memory, owned by the plan)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -98,54 +96,58 @@ __device__ __forceinline__ long tc_out_index(const ConvArgs& a, long b, int j, i
 }
 
 // ---------------------------------------------------------------------------------------------- weight packing
-// wp[block][cb][k][h][n_pad][4]  (cb = KC-channel block of the reduction channels, h = 16-byte chunk inside it)
-//   fprop: block = CSR position (j, n), rows = out channels o, reduction channels = in channels c.
-//   dgrad: block = transposed-CSR position (n, j), rows = in channels c, reduction channels = out channels o.
-// One CTA reads the contiguous ci*K run(s) of the dense weight for its output channel(s) (coalesced) and scatters 16-byte
-// groups.  Padding rows / channels are never written: the packed buffer is zero-filled once when it is allocated.
-__global__ void __launch_bounds__(128) conv_pack_kernel(ConvArgs a, const float* __restrict__ w, float4* __restrict__ wp,
-                                                        int mode, int n_pad, int ck_pad, int KC) {
-  extern __shared__ float rows[];               // mode 0: [ci*K]   mode 1: [4][ci*K]
+// Packed layout (per mode): for joint group g and K-side joint n with `cnt` consuming joints ("slots") in the group, one
+// contiguous piece per K-chunk cb:   piece(g, n, cb) = [tap k][chunk h][slot][n_pad rows][4 reduction channels]
+// so that (a) a pipeline stage needs ONE bulk copy for all its weights and (b) the rows of consecutive slots are contiguous,
+// i.e. one tcgen05.mma can cover several output joints (N = len * n_pad).
+//   fprop: rows = out channels o of joint j, reduction = in channels c of joint n.
+//   dgrad: rows = in channels c of joint n,  reduction = out channels o of joint j.
+// One CTA reads the contiguous ci*K runs of 4 consecutive output channels of block (j, n) once (coalesced) and writes both
+// copies.  Padding rows / channels are never written: the packed buffers are zero-filled once at allocation.
+struct TcPk { int base_f, cnt_f, slot_f, base_d, cnt_d, slot_d; };
+
+__global__ void __launch_bounds__(128) conv_pack_kernel(ConvArgs a, const float* __restrict__ w, float4* __restrict__ wp_f,
+                                                        float4* __restrict__ wp_d, const TcPk* __restrict__ pk, int npad_f,
+                                                        int kc_f, int npad_d, int kc_d) {
+  extern __shared__ float rows[];               // [4][ci*K]
   const int Cin = a.J * a.ci;
   const int run = a.ci * a.K;
-  const int qpb = KC / 4, ncb = ck_pad / KC;
-  if (mode == 0) {
-    const int blk = blockIdx.x / a.co, o = blockIdx.x % a.co;
-    const int j = a.blk_j[blk], n = a.blk_n[blk];
-    const float* src = w + ((long)(j * a.co + o) * Cin + n * a.ci) * a.K;
-    for (int e = threadIdx.x; e < run; e += blockDim.x) rows[e] = src[e];
-    __syncthreads();
-    const int nq = (a.ci + 3) / 4;
-    for (int it = threadIdx.x; it < nq * a.K; it += blockDim.x) {
-      const int k = it % a.K, q = it / a.K;
+  const int no4 = (a.co + 3) / 4;
+  const int blk = blockIdx.x / no4, o4 = blockIdx.x % no4;
+  const int j = a.blk_j[blk], n = a.blk_n[blk];
+  const TcPk e = pk[blk];
+  for (int i = 0; i < 4; ++i) {
+    const int o = o4 * 4 + i;
+    if (o < a.co) {
+      const float* src = w + ((long)(j * a.co + o) * Cin + n * a.ci) * a.K;
+      for (int x = threadIdx.x; x < run; x += blockDim.x) rows[i * run + x] = __uint_as_float(to_tf32(src[x]));
+    } else {
+      for (int x = threadIdx.x; x < run; x += blockDim.x) rows[i * run + x] = 0.f;
+    }
+  }
+  __syncthreads();
+  if (wp_f) {   // rows = o (4 of them), 16-byte groups over c
+    const int qpb = kc_f / 4, nq = (a.ci + 3) / 4;
+    for (int it = threadIdx.x; it < 4 * nq * a.K; it += blockDim.x) {
+      const int k = it % a.K;
+      const int q = (it / a.K) % nq;
+      const int i = it / (a.K * nq);
+      const int o = o4 * 4 + i;
+      if (o >= a.co) continue;
       float v[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = (q * 4 + i < a.ci) ? __uint_as_float(to_tf32(rows[(q * 4 + i) * a.K + k])) : 0.f;
+      for (int c = 0; c < 4; ++c) v[c] = (q * 4 + c < a.ci) ? rows[i * run + (q * 4 + c) * a.K + k] : 0.f;
       const int cb = q / qpb, h = q % qpb;
-      wp[((((long)blk * ncb + cb) * a.K + k) * qpb + h) * n_pad + o] = make_float4(v[0], v[1], v[2], v[3]);
+      wp_f[(long)e.base_f + ((long)((cb * a.K + k) * qpb + h) * e.cnt_f + e.slot_f) * npad_f + o] = make_float4(v[0], v[1], v[2], v[3]);
     }
-  } else {
-    const int no4 = (a.co + 3) / 4;
-    const int blk = blockIdx.x / no4, o4 = blockIdx.x % no4;
-    int n = 0;
-    while (a.nbT_off[n + 1] <= blk) ++n;
-    const int j = a.nbT_idx[blk];
-    for (int i = 0; i < 4; ++i) {
-      const int o = o4 * 4 + i;
-      if (o < a.co) {
-        const float* src = w + ((long)(j * a.co + o) * Cin + n * a.ci) * a.K;
-        for (int e = threadIdx.x; e < run; e += blockDim.x) rows[i * run + e] = src[e];
-      } else {
-        for (int e = threadIdx.x; e < run; e += blockDim.x) rows[i * run + e] = 0.f;
-      }
-    }
-    __syncthreads();
+  }
+  if (wp_d) {   // rows = c, 16-byte group = the 4 output channels of this CTA
+    const int qpb = kc_d / 4;
     const int cb = o4 / qpb, h = o4 % qpb;
     for (int it = threadIdx.x; it < run; it += blockDim.x) {
       const int k = it % a.K, c = it / a.K;
-      const float4 v = make_float4(__uint_as_float(to_tf32(rows[0 * run + it])), __uint_as_float(to_tf32(rows[1 * run + it])),
-                                   __uint_as_float(to_tf32(rows[2 * run + it])), __uint_as_float(to_tf32(rows[3 * run + it])));
-      wp[((((long)blk * ncb + cb) * a.K + k) * qpb + h) * n_pad + c] = v;
+      wp_d[(long)e.base_d + ((long)((cb * a.K + k) * qpb + h) * e.cnt_d + e.slot_d) * npad_d + c] =
+          make_float4(rows[it], rows[run + it], rows[2 * run + it], rows[3 * run + it]);
     }
   }
 }
@@ -202,15 +204,16 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(TcArgs p, const float
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
-// which (local out joint, packed weight block) pairs consume the activation tile of K-side joint n, for one joint group
+// per joint group: which K-side joints' tiles are consumed, where their packed weights are, and the runs of consecutive
+// local output joints (one MMA each)
 struct TcWorkG {
   int cnt[64];
-  unsigned char jl[64][TC_MAX_NB];
-  int blk[64][TC_MAX_NB];
+  int base[64];                 // float4 offset of piece (g, n, cb = 0)
+  int nruns[64];
+  unsigned int run[64][4];      // slot_first | jl_first << 8 | len << 16
 };
 struct TcWork {
   TcWorkG g;
-  unsigned int started;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const unsigned char* __restrict__ astage,
@@ -252,8 +255,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tap_bytes = (uint32_t)qpb * p.n_pad * 16;   // one tap of a weight piece: qpb chunks x n_pad rows x 16 B
-  const uint32_t piece = (uint32_t)a.K * tap_bytes;          // one (slot) weight piece of a stage: all K taps, contiguous
+  if (warp >= 2) {
+    // zero the accumulators once: every MMA then accumulates, so one instruction may span several output joints
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int c = 0; c < p.tmem_cols; c += 16) {
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(tmem_base + lane_base + c),
+          "r"(0)
+          : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t slot_u = (uint32_t)p.n_pad;                 // 16-byte units per slot inside one (tap, chunk) row block
   const int si_beg = blockIdx.z * p.split_len, si_end = si_beg + p.split_len;
 
   if (warp == 0) {
@@ -268,22 +284,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* st = smem_raw + (size_t)s * p.stage_bytes;
         if (lane == 0) {
-          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.a_bytes + (uint32_t)cnt * piece);
+          const uint32_t wbytes = (uint32_t)a.K * qpb * cnt * p.n_pad * 16;      // all slots of this stage, contiguous
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.a_bytes + wbytes);
           bulk_g2s(st, astage + (((size_t)mt * a.J + n) * ncb + cb) * p.a_bytes, (uint32_t)p.a_bytes, &full_bar[s]);
+          bulk_g2s(st + p.a_bytes, reinterpret_cast<const unsigned char*>(wp) + ((size_t)work.g.base[n] * 16 + (size_t)cb * wbytes),
+                   wbytes, &full_bar[s]);
         }
         __syncwarp();
-        if (lane < cnt) {
-          const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(wp) + ((size_t)work.g.blk[n][lane] * ncb + cb) * piece;
-          bulk_g2s(st + p.a_bytes + (size_t)lane * piece, gsrc, piece, &full_bar[s]);
-        }
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);      // N is filled in per run
     int s = 0, si = 0;
-    uint32_t ph = 0, started = 0;
+    uint32_t ph = 0;
     for (int n = 0; n < a.J; ++n) {
       const int cnt = work.g.cnt[n];
       if (cnt == 0) continue;
@@ -299,30 +314,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
           //   fprop stride 1: tap k reads rows shifted by k*Bt           -> one run  k = 0..K-1,      a += Bt
           //   fprop stride 2: even taps read phase 0, odd taps phase 1    -> two runs (k even / odd),  a += Bt, b += 2 taps
           //   dgrad         : tap k reads rows shifted by (K-1-k)*Bt      -> one run  k = 0..K-1,      a -= Bt
+          // B rows of consecutive slots are contiguous: one MMA covers a whole run of consecutive output joints.
+          const uint32_t row_u = (uint32_t)cnt * slot_u;                       // 16-byte units of one (tap, chunk) row block
           const uint64_t adesc0 = tc_desc(a_base, (uint32_t)p.rows_alloc * 16, 128);
-          const uint64_t bdesc0 = tc_desc(b_base, (uint32_t)p.n_pad * 16, 128);
-          const uint64_t a_kk = 2u * (uint32_t)p.rows_alloc, b_kk = 2u * (uint32_t)p.n_pad;   // next 8 reduction channels
-          const uint32_t tap_u = tap_bytes >> 4, piece_u = piece >> 4;
-          const int nrun = (p.mode == 0 && a.s == 2) ? 2 : 1;
+          const uint64_t bdesc0 = tc_desc(b_base, row_u * 16, 128);
+          const uint64_t a_kk = 2u * (uint32_t)p.rows_alloc, b_kk = 2u * row_u;   // next 8 reduction channels
+          const uint32_t tap_u = (uint32_t)qpb * row_u;
+          const int ntaprun = (p.mode == 0 && a.s == 2) ? 2 : 1;
           const int nkk = qpb / 2;
-          for (int e = 0; e < cnt; ++e) {
-            const int jl = work.g.jl[n][e];
-            const uint32_t d_addr = tmem_base + (uint32_t)(jl * p.n_pad);
-            uint32_t acc = (started >> jl) & 1u;
-            started |= 1u << jl;
-            for (int run = 0; run < nrun; ++run) {
-              uint64_t ad, bd = bdesc0 + (uint64_t)((uint32_t)e * piece_u + (uint32_t)run * tap_u);
+          for (int r = 0; r < work.g.nruns[n]; ++r) {
+            const uint32_t rr = work.g.run[n][r];
+            const uint32_t slot0 = rr & 0xff, jl0 = (rr >> 8) & 0xff, len = rr >> 16;
+            const uint32_t d_addr = tmem_base + jl0 * (uint32_t)p.n_pad;
+            const uint32_t idesc = idesc0 | (((len * (uint32_t)p.n_pad) >> 3) << 17);
+            for (int run = 0; run < ntaprun; ++run) {
+              uint64_t ad, bd = bdesc0 + (uint64_t)(slot0 * slot_u + (uint32_t)run * tap_u);
               long a_step;
               int ntap;
               if (p.mode == 1) { ad = adesc0 + (uint32_t)((a.K - 1) * p.Bt); a_step = -(long)p.Bt; ntap = a.K; }
-              else if (nrun == 1) { ad = adesc0; a_step = p.Bt; ntap = a.K; }
+              else if (ntaprun == 1) { ad = adesc0; a_step = p.Bt; ntap = a.K; }
               else { ad = adesc0 + (uint32_t)(run * p.Tp2 * p.Bt); a_step = p.Bt; ntap = (a.K - run + 1) / 2; }
-              const uint64_t b_step = (uint64_t)tap_u * nrun;
+              const uint64_t b_step = (uint64_t)tap_u * ntaprun;
               if (nkk == 1) {
 #pragma unroll 5
                 for (int tp = 0; tp < ntap; ++tp) {
-                  tc_mma_tf32(d_addr, ad, bd, idesc, acc);
-                  acc = 1;
+                  tc_mma_tf32(d_addr, ad, bd, idesc, 1u);
                   ad += a_step;
                   bd += b_step;
                 }
@@ -331,8 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
                   uint64_t ad2 = ad, bd2 = bd;
 #pragma unroll 4
                   for (int kk = 0; kk < nkk; ++kk) {
-                    tc_mma_tf32(d_addr, ad2, bd2, idesc, acc);
-                    acc = 1;
+                    tc_mma_tf32(d_addr, ad2, bd2, idesc, 1u);
                     ad2 += a_kk;
                     bd2 += b_kk;
                   }
@@ -348,11 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
-    if (lane == 0) {
-      work.started = started;
-      __threadfence_block();
-      tc_commit(&accum_bar);
-    }
+    if (lane == 0) tc_commit(&accum_bar);
     __syncwarp();
   } else {
     // =============================== epilogue (warps 2..5) ===============================
@@ -362,16 +373,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
     float* outs = reinterpret_cast<float*>(smem_raw);          // [gj * n_real][128]   (stage buffers are free now)
     const int lq = warp & 3;
     const int m = lq * 32 + lane;
-    const unsigned int started = *reinterpret_cast<volatile unsigned int*>(&work.started);
     for (int jl = 0; jl < gj; ++jl) {
       for (int c16 = 0; c16 < p.n_pad; c16 += 16) {
         float v[16];
-        if ((started >> jl) & 1u) {
-          tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(jl * p.n_pad + c16), v);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        }
+        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(jl * p.n_pad + c16), v);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (c16 + i < p.n_real) outs[(size_t)(jl * p.n_real + c16 + i) * 128 + m] = v[i];
@@ -481,6 +486,137 @@ static int tc_pick_kc(int ck_pad, int n_pad, int K) {
   return 8;
 }
 
+// Batch-independent description of one (plan, mode): channel padding, joint groups, packed-weight layout, work tables.
+struct TcLayer {
+  bool ok;
+  int n_real, n_pad, ck, ck_pad, KC, GJ, groups, nbmax, longest;
+  long packed_f4;                       // size of the packed weights in float4
+  TcWorkG* dev_work;                    // [groups]
+  std::vector<std::vector<int>> slots;  // [g * J + n] -> local joints jl (ascending) consuming tile n
+  std::vector<long> base;               // [g * J + n] -> float4 offset of piece (g, n, 0)
+};
+struct TcLayers {
+  TcLayer m[2];
+  TcPk* dev_pk;
+};
+
+static void tc_build_layer(const hmvae_conv_plan* plan, int mode, TcLayer* L) {
+  const ConvArgs& a = plan->a;
+  L->ok = false;
+  L->dev_work = nullptr;
+  L->n_real = mode == 0 ? a.co : a.ci;
+  L->ck = mode == 0 ? a.ci : a.co;
+  L->n_pad = rup(L->n_real, 16);
+  L->ck_pad = rup(L->ck, 8);
+  if (a.J > 64 || L->n_pad > 256) return;
+  L->KC = tc_pick_kc(L->ck_pad, L->n_pad, a.K);
+  L->GJ = 64 / L->n_pad;
+  if (L->GJ < 1) L->GJ = 1;
+  if (L->GJ > 4) L->GJ = 4;
+  if (L->GJ > a.J) L->GJ = a.J;
+  L->groups = (a.J + L->GJ - 1) / L->GJ;
+  // N-side joint -> K-side joints (fprop: neighbour list; dgrad: transpose, ascending)
+  std::vector<std::vector<int>> lists(a.J);
+  for (int j = 0; j < a.J; ++j)
+    for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m) {
+      if (mode == 0) lists[j].push_back(plan->nb_idx[m]);
+      else lists[plan->nb_idx[m]].push_back(j);
+    }
+  const int ncb = L->ck_pad / L->KC, qpb = L->KC / 4;
+  L->slots.assign((size_t)L->groups * a.J, {});
+  L->base.assign((size_t)L->groups * a.J, 0);
+  std::vector<TcWorkG> host(L->groups);
+  long off = 0;
+  L->nbmax = 0;
+  L->longest = 0;
+  for (int g = 0; g < L->groups; ++g) {
+    TcWorkG& w = host[g];
+    memset(&w, 0, sizeof(w));
+    int stages = 0;
+    for (int n = 0; n < a.J; ++n) {
+      std::vector<int>& sl = L->slots[(size_t)g * a.J + n];
+      for (int jl = 0; jl < L->GJ && g * L->GJ + jl < a.J; ++jl)
+        for (int kn : lists[g * L->GJ + jl])
+          if (kn == n) sl.push_back(jl);
+      const int cnt = (int)sl.size();
+      w.cnt[n] = cnt;
+      w.base[n] = (int)off;
+      L->base[(size_t)g * a.J + n] = off;
+      if (cnt == 0) continue;
+      if (cnt > L->nbmax) L->nbmax = cnt;
+      stages += ncb;
+      int nr = 0;
+      for (int i = 0; i < cnt;) {
+        int len = 1;
+        while (i + len < cnt && sl[i + len] == sl[i] + len) ++len;
+        w.run[n][nr++] = (unsigned)i | ((unsigned)sl[i] << 8) | ((unsigned)len << 16);
+        i += len;
+      }
+      w.nruns[n] = nr;
+      off += (long)ncb * a.K * qpb * cnt * L->n_pad;
+    }
+    if (stages > L->longest) L->longest = stages;
+  }
+  if (off * 16 >= (1L << 31)) return;
+  L->packed_f4 = off;
+  if (cudaMalloc(&L->dev_work, L->groups * sizeof(TcWorkG)) != cudaSuccess) return;
+  if (cudaMemcpy(L->dev_work, host.data(), L->groups * sizeof(TcWorkG), cudaMemcpyHostToDevice) != cudaSuccess) return;
+  L->ok = true;
+}
+
+static const TcLayers* tc_layers(const hmvae_conv_plan* plan) {
+  auto it = plan->tc_tables.find(0);
+  if (it != plan->tc_tables.end()) return reinterpret_cast<const TcLayers*>(it->second);
+  TcLayers* LL = new TcLayers();
+  tc_build_layer(plan, 0, &LL->m[0]);
+  tc_build_layer(plan, 1, &LL->m[1]);
+  LL->dev_pk = nullptr;
+  const ConvArgs& a = plan->a;
+  if (LL->m[0].ok && LL->m[1].ok) {
+    std::vector<TcPk> pk(a.nnz);
+    for (int j = 0; j < a.J; ++j)
+      for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m) {
+        const int n = plan->nb_idx[m];
+        TcPk e;
+        {
+          const TcLayer& L = LL->m[0];
+          const int g = j / L.GJ, jl = j % L.GJ;
+          const std::vector<int>& sl = L.slots[(size_t)g * a.J + n];
+          e.base_f = (int)L.base[(size_t)g * a.J + n];
+          e.cnt_f = (int)sl.size();
+          e.slot_f = 0;
+          for (size_t i = 0; i < sl.size(); ++i) if (sl[i] == jl) e.slot_f = (int)i;
+        }
+        {
+          const TcLayer& L = LL->m[1];
+          const int g = n / L.GJ, nl = n % L.GJ;
+          const std::vector<int>& sl = L.slots[(size_t)g * a.J + j];
+          e.base_d = (int)L.base[(size_t)g * a.J + j];
+          e.cnt_d = (int)sl.size();
+          e.slot_d = 0;
+          for (size_t i = 0; i < sl.size(); ++i) if (sl[i] == nl) e.slot_d = (int)i;
+        }
+        pk[m] = e;
+      }
+    if (cudaMalloc(&LL->dev_pk, pk.size() * sizeof(TcPk)) != cudaSuccess ||
+        cudaMemcpy(LL->dev_pk, pk.data(), pk.size() * sizeof(TcPk), cudaMemcpyHostToDevice) != cudaSuccess)
+      LL->m[0].ok = LL->m[1].ok = false;
+  }
+  plan->tc_tables[0] = LL;
+  return LL;
+}
+
+void conv_tc_release(const hmvae_conv_plan* plan) {
+  auto it = plan->tc_tables.find(0);
+  if (it == plan->tc_tables.end()) return;
+  TcLayers* LL = reinterpret_cast<TcLayers*>(it->second);
+  for (int m = 0; m < 2; ++m)
+    if (LL->m[m].dev_work) cudaFree(LL->m[m].dev_work);
+  if (LL->dev_pk) cudaFree(LL->dev_pk);
+  delete LL;
+  plan->tc_tables.erase(it);
+}
+
 static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out);
 
 // geometry is a pure function of (plan, mode, B, T): memoised, so the per-call host cost is one map lookup
@@ -500,27 +636,20 @@ static bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcA
 
 static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out) {
   const ConvArgs& a = plan->a;
-  const hmvae_conv_desc& d = plan->d;
-  if (a.J > 64) return false;
+  const TcLayer& L = tc_layers(plan)->m[mode];
+  if (!L.ok) return false;
   TcArgs p;
+  memset(&p, 0, sizeof(p));
   p.a = a;
   p.mode = mode;
   p.B = B;
   p.T = T;
-  p.T_out = conv_t_out(d, T);
+  p.T_out = conv_t_out(plan->d, T);
   const int Tq = T + 2 * a.p;
-  if (mode == 0) {
-    p.off = a.nb_off; p.idx = a.nb_idx;
-    p.n_real = a.co; p.ck = a.ci;
-    p.Tt = p.T_out;
-  } else {
-    p.off = a.nbT_off; p.idx = a.nbT_idx;
-    p.n_real = a.ci; p.ck = a.co;
-    p.Tt = Tq;
-  }
-  p.n_pad = rup(p.n_real, 16);
-  p.ck_pad = rup(p.ck, 8);
-  if (p.Tt > 128 || p.Tt < 1 || p.n_pad > 256) return false;
+  p.Tt = (mode == 0) ? p.T_out : Tq;
+  p.n_real = L.n_real; p.n_pad = L.n_pad; p.ck = L.ck; p.ck_pad = L.ck_pad; p.KC = L.KC; p.GJ = L.GJ; p.nbmax = L.nbmax;
+  p.wtab = L.dev_work;
+  if (p.Tt > 128 || p.Tt < 1) return false;
   p.Bt = 128 / p.Tt;
   if (p.Bt > B) p.Bt = B;
   p.Tp2 = (Tq + 1) / 2;
@@ -540,107 +669,25 @@ static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mod
   p.rows_alloc = rup(p.rows_alloc, 8);
   if (p.rows_alloc * 16 >= (1 << 18)) return false;
   p.mtiles = (B + p.Bt - 1) / p.Bt;
-  const int budget = 208 * 1024;
-  p.KC = tc_pick_kc(p.ck_pad, p.n_pad, a.K);
   p.a_bytes = (p.KC / 4) * p.rows_alloc * 16;
-  std::vector<std::vector<int>> lists(a.J);
-  for (int j = 0; j < a.J; ++j)
-    for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m) {
-      if (mode == 0) lists[j].push_back(plan->nb_idx[m]);
-      else lists[plan->nb_idx[m]].push_back(j);
-    }
-  int gj_max = 512 / p.n_pad;
-  if (gj_max > a.J) gj_max = a.J;
-  if (gj_max > TC_MAX_GJ) gj_max = TC_MAX_GJ;
-  bool found = false;
-  for (int GJ = gj_max; GJ >= 1 && !found; --GJ) {
-    int nbmax = 0;
-    for (int g0 = 0; g0 < a.J; g0 += GJ) {
-      std::vector<int> cnt(a.J, 0);
-      for (int j = g0; j < a.J && j < g0 + GJ; ++j)
-        for (int n : lists[j]) cnt[n]++;
-      for (int n = 0; n < a.J; ++n) nbmax = cnt[n] > nbmax ? cnt[n] : nbmax;
-    }
-    if (nbmax > TC_MAX_NB) continue;
-    const int ctas = p.mtiles * ((a.J + GJ - 1) / GJ);
-    if (ctas < 96 && GJ > 1) continue;            // prefer filling the 148 SMs over sharing tiles inside a CTA
-    const int stage = rup(p.a_bytes + nbmax * a.K * (p.KC / 4) * p.n_pad * 16, 128);
-    const int epi = GJ * p.n_real * 128 * 4;
-    int stages = budget / stage;
-    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    if (stages < 2 || epi > stages * stage) continue;
-    p.GJ = GJ; p.nbmax = nbmax; p.stages = stages; p.stage_bytes = stage;
-    found = true;
-  }
-  if (!found) return false;
-  {
-    // split-K: longest per-CTA stage sequence over the groups, cut so that the grid reaches ~2 CTAs per SM
-    int longest = 0;
-    for (int g0 = 0; g0 < a.J; g0 += p.GJ) {
-      std::vector<int> used(a.J, 0);
-      for (int j = g0; j < a.J && j < g0 + p.GJ; ++j)
-        for (int n : lists[j]) used[n] = 1;
-      int c = 0;
-      for (int n = 0; n < a.J; ++n) c += used[n];
-      c *= p.ck_pad / p.KC;
-      longest = c > longest ? c : longest;
-    }
-    const int ctas = p.mtiles * ((a.J + p.GJ - 1) / p.GJ);
-    int splits = num_sms() / ctas;                         // fill one wave of SMs, no more (fixed per-CTA cost dominates)
-    if (splits > longest / 3) splits = longest / 3;        // at least 3 stages per CTA
-    if (splits < 1) splits = 1;
-    if (splits > 64) splits = 64;
-    p.split_len = (longest + splits - 1) / splits;
-    p.splits = (longest + p.split_len - 1) / p.split_len;
-  }
-  {
-    const int key = mode * 1000 + p.GJ;
-    auto it = plan->tc_tables.find(key);
-    if (it == plan->tc_tables.end()) {
-      const int groups = (a.J + p.GJ - 1) / p.GJ;
-      std::vector<TcWorkG> host(groups);
-      // CSR of the N-side joints (fprop: nb lists; dgrad: transpose), block index = CSR position
-      std::vector<int> off(a.J + 1, 0), idx;
-      if (mode == 0) {
-        off = plan->nb_off;
-        idx = plan->nb_idx;
-      } else {
-        for (int n = 0; n < a.J; ++n) {
-          for (int j = 0; j < a.J; ++j)
-            for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m)
-              if (plan->nb_idx[m] == n) idx.push_back(j);
-          off[n + 1] = (int)idx.size();
-        }
-      }
-      for (int g = 0; g < groups; ++g) {
-        TcWorkG& w = host[g];
-        memset(&w, 0, sizeof(w));
-        for (int jl = 0; jl < p.GJ && g * p.GJ + jl < a.J; ++jl) {
-          const int j = g * p.GJ + jl;
-          for (int m = off[j]; m < off[j + 1]; ++m) {
-            const int n = idx[m];
-            if (w.cnt[n] < TC_MAX_NB) {
-              w.jl[n][w.cnt[n]] = (unsigned char)jl;
-              w.blk[n][w.cnt[n]] = m;
-              w.cnt[n]++;
-            }
-          }
-        }
-      }
-      void* dev = nullptr;
-      if (cudaMalloc(&dev, groups * sizeof(TcWorkG)) != cudaSuccess) return false;
-      if (cudaMemcpy(dev, host.data(), groups * sizeof(TcWorkG), cudaMemcpyHostToDevice) != cudaSuccess) {
-        cudaFree(dev);
-        return false;
-      }
-      it = plan->tc_tables.emplace(key, dev).first;
-    }
-    p.wtab = reinterpret_cast<const TcWorkG*>(it->second);
-  }
+  p.stage_bytes = rup(p.a_bytes + L.nbmax * a.K * (p.KC / 4) * p.n_pad * 16, 128);
+  const int budget = 208 * 1024;
+  p.stages = budget / p.stage_bytes;
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  const int epi = p.GJ * p.n_real * 128 * 4;
+  if (p.stages < 2 || epi > p.stages * p.stage_bytes) return false;
   int cols = p.GJ * p.n_pad, pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   if (pow2 > 512) return false;
   p.tmem_cols = pow2;
+  // split-K so that the grid fills one wave of SMs (fixed per-CTA cost dominates beyond that); >= 3 stages per CTA
+  const int ctas = p.mtiles * L.groups;
+  int splits = num_sms() / ctas;
+  if (splits > L.longest / 3) splits = L.longest / 3;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  p.split_len = (L.longest + splits - 1) / splits;
+  p.splits = (L.longest + p.split_len - 1) / p.split_len;
   *out = p;
   return true;
 }
@@ -663,32 +710,22 @@ long conv_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T, int mode
 }
 
 void conv_packed_sizes(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad) {
-  const ConvArgs& a = plan->a;
-  *n_fprop = (long)a.nnz * a.K * rup(a.ci, 8) * rup(a.co, 16);
-  *n_dgrad = (long)a.nnz * a.K * rup(a.co, 8) * rup(a.ci, 16);
+  const TcLayers* LL = tc_layers(plan);
+  *n_fprop = LL->m[0].ok ? LL->m[0].packed_f4 * 4 : 0;
+  *n_dgrad = LL->m[1].ok ? LL->m[1].packed_f4 * 4 : 0;
 }
 
 int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* wp_d, cudaStream_t st) {
   const ConvArgs& a = plan->a;
-  if (wp_f) {
-    const int n_pad = rup(a.co, 16), ck_pad = rup(a.ci, 8);
-    const size_t smem = (size_t)a.ci * a.K * 4;
-    conv_pack_kernel<<<a.nnz * a.co, 128, smem, st>>>(a, w, reinterpret_cast<float4*>(wp_f), 0, n_pad, ck_pad,
-                                                      tc_pick_kc(ck_pad, n_pad, a.K));
-    int rc = check_launch("conv_pack(fprop)");
-    if (rc) return rc;
-  }
-  if (wp_d) {
-    const int n_pad = rup(a.ci, 16), ck_pad = rup(a.co, 8);
-    const size_t smem = (size_t)4 * a.ci * a.K * 4;
-    if (smem > 48 * 1024)
-      HMVAE_CUDA(cudaFuncSetAttribute(conv_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_pack_kernel<<<a.nnz * ((a.co + 3) / 4), 128, smem, st>>>(a, w, reinterpret_cast<float4*>(wp_d), 1, n_pad, ck_pad,
-                                                                 tc_pick_kc(ck_pad, n_pad, a.K));
-    int rc = check_launch("conv_pack(dgrad)");
-    if (rc) return rc;
-  }
-  return 0;
+  const TcLayers* LL = tc_layers(plan);
+  if (!LL->m[0].ok || !LL->m[1].ok || !LL->dev_pk) return fail_arg("conv_pack_weights: layer not supported by the tcgen05 path");
+  if (!wp_f && !wp_d) return 0;
+  if ((wp_f && !aligned16(wp_f)) || (wp_d && !aligned16(wp_d))) return fail_arg("conv_pack_weights: buffers must be 16-byte aligned");
+  const size_t smem = (size_t)4 * a.ci * a.K * 4;
+  if (smem > 48 * 1024) HMVAE_CUDA(cudaFuncSetAttribute(conv_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_pack_kernel<<<a.nnz * ((a.co + 3) / 4), 128, smem, st>>>(a, w, reinterpret_cast<float4*>(wp_f), reinterpret_cast<float4*>(wp_d),
+                                                               LL->dev_pk, LL->m[0].n_pad, LL->m[0].KC, LL->m[1].n_pad, LL->m[1].KC);
+  return check_launch("conv_pack");
 }
 
 int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, const float* wp,

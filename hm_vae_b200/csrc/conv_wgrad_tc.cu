@@ -148,22 +148,27 @@ __global__ void __launch_bounds__(256) conv_wgrad_prep_kernel(WgArgs p, const fl
   }
 }
 
-// db[j*co + o] = sum_{b,t} dy * lrelu'(y)          (one warp per channel)
-__global__ void conv_bias_grad_kernel(ConvArgs a, const float* __restrict__ dy, const float* __restrict__ yact,
-                                      float* __restrict__ db, int B, int T_out, int accumulate) {
-  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (ch >= a.J * a.co) return;
+// db[j*co + o] = sum_{b,t} dy * lrelu'(y)          (one 128-thread CTA per channel, coalesced along t, fixed-order reduction)
+__global__ void __launch_bounds__(128) conv_bias_grad_kernel(ConvArgs a, const float* __restrict__ dy,
+                                                             const float* __restrict__ yact, float* __restrict__ db, int B,
+                                                             int T_out, int accumulate) {
+  __shared__ float red[4];
+  const int ch = blockIdx.x;
   const int j = ch / a.co, o = ch % a.co;
   float acc = 0.f;
-  for (int e = lane; e < B * T_out; e += 32) {
+  for (int e = threadIdx.x; e < B * T_out; e += 128) {
     const long oi = wg_out_index(a, e / T_out, j, o, e % T_out, T_out);
     float g = dy[oi];
     if (a.lrelu && !(yact[oi] > 0.f)) g *= 0.2f;
     acc += g;
   }
   acc = warp_sum(acc);
-  if (lane == 0) db[ch] = accumulate ? db[ch] + acc : acc;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float s = (red[0] + red[1]) + (red[2] + red[3]);
+    db[ch] = accumulate ? db[ch] + s : s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
@@ -446,7 +451,7 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
   }
   if (dbias) {
     const int ch = p.a.J * p.a.co;
-    conv_bias_grad_kernel<<<(ch + 3) / 4, 128, 0, st>>>(p.a, dy, yact, dbias, B, p.T_out, accumulate);
+    conv_bias_grad_kernel<<<ch, 128, 0, st>>>(p.a, dy, yact, dbias, B, p.T_out, accumulate);
     int rc = check_launch("conv_bias_grad");
     if (rc) return rc;
   }

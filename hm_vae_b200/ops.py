@@ -365,6 +365,37 @@ def angle_axis_to_rotation_matrix(angle_axis):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ latent heads
+class _LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).contiguous()
+        rows, in_f, out_f = x2.shape[0], x2.shape[1], weight.shape[0]
+        y = torch.empty((rows, out_f), device=x.device, dtype=torch.float32)
+        w = weight.contiguous()
+        check(lib.hmvae_linear_fwd(ptr(x2), ptr(w), ptr(bias), ptr(y), rows, in_f, out_f, stream()), "linear_fwd")
+        ctx.save_for_backward(x2, w)
+        ctx.shape, ctx.has_bias = shape, bias is not None
+        return y.view(*shape[:-1], out_f)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w = ctx.saved_tensors
+        rows, in_f, out_f = x2.shape[0], x2.shape[1], w.shape[0]
+        gy2 = gy.reshape(rows, out_f).contiguous()
+        gx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        gb = torch.empty(out_f, device=w.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        check(lib.hmvae_linear_bwd(ptr(x2), ptr(w), ptr(gy2), ptr(gx), ptr(gw), ptr(gb), rows, in_f, out_f, stream()), "linear_bwd")
+        return (gx.view(ctx.shape) if gx is not None else None), gw, gb
+
+
+def linear(x, weight, bias=None):
+    """F.linear on the library's own fp32 kernels (the latent heads of the hierarchy)."""
+    return _LinearFn.apply(x, weight, bias)
+
+
 # ------------------------------------------------------------------------------------------------ VAE latent
 class _LatentFn(Function):
     """z = eps*exp(lv/2)+mu and the KL row-sum (seq_two_hier_sa_vae.py:419-428); dist is [rows, 2d] = (mu | lv)."""

@@ -107,7 +107,8 @@ class Encoder(nn.Module):
                 continue
             bs = input.shape[0]
             k_edges = input.shape[1] // self.channel_base[i + 1]
-            z_vector_list.append(self.latent_enc_layers[i](input.view(bs, k_edges, -1)))
+            head = self.latent_enc_layers[i]
+            z_vector_list.append(ops.linear(input.view(bs, k_edges, -1), head.weight, head.bias))
         return input, z_vector_list
 
 
@@ -183,7 +184,8 @@ class Decoder(nn.Module):
 
         def feats(z_idx):
             z = z_vec_list[n - z_idx - 1]
-            f = self.latent_dec_layers[z_idx](z)
+            head = self.latent_dec_layers[z_idx]
+            f = ops.linear(z, head.weight, head.bias)
             return f.view(z.size(0), -1, self.timestep_list[z_idx])
 
         x = feats(0)

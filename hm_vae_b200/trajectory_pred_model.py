@@ -103,7 +103,7 @@ class TrajectoryModel(nn.Module):
         dev = encoder_input.device
         latent = self.enc(ops.transpose_ct(encoder_input))             # bs X (7*d) X T
         feat = ops.transpose_ct(latent)                                # bs X T X (7*d)   (edge-major, channel-minor)
-        root_v_out = self.fc_mapping(feat)                             # bs X T X 3
+        root_v_out = ops.linear(feat, self.fc_mapping.weight, self.fc_mapping.bias)   # bs X T X 3
 
         sums = torch.zeros(2, device=dev, dtype=torch.float32)
         w_t = hp['rec_root_trans_w'] if hp['use_accumulation_root_v'] else 0.0

@@ -175,6 +175,14 @@ int hmvae_traj_fwdbwd(const float* root_v_pred, const float* root_v_gt, const fl
                       int batch, int t, int joints, float sv, float st, float* losses, float* d_root_v,
                       void* stream);
 
+/* ------------------------------------------------------------------ latent heads (nn.Linear) */
+
+/* y[rows, out_f] = x[rows, in_f] w[out_f, in_f]^T + bias   (seq_two_hier_sa_vae.py:162, 267); fp32 CUDA cores. */
+int hmvae_linear_fwd(const float* x, const float* w, const float* bias, float* y, int rows, int in_f, int out_f, void* stream);
+/* dx = dy w, dw = dy^T x, db = column sums of dy; any of dx / dw / db may be NULL. */
+int hmvae_linear_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int rows, int in_f,
+                     int out_f, void* stream);
+
 /* ------------------------------------------------------------------ optimiser */
 
 /* torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, eps outside sqrt):

@@ -405,3 +405,19 @@ def test_trajectory_step_vs_reference_golden(golden_models, smpl, impl):
             _close_cks(_cks(p.grad.cpu()), g[f"traj_grad/{k}"], gtol, k)
     assert rel_l2(model.fc_mapping.bias.grad.cpu(), g["traj_gb_fc"]) < btol
     ops.set_conv_impl(ops.IMPL_AUTO)
+
+
+@pytest.mark.parametrize("rows,i,o", [((32, 14), 384, 24), ((5, 7), 24, 384), ((3,), 33, 5)])
+def test_linear_vs_oracle(rows, i, o):
+    gen = torch.Generator().manual_seed(i + o)
+    x = torch.randn(*rows, i, generator=gen)
+    w = torch.randn(o, i, generator=gen)
+    b = torch.randn(o, generator=gen)
+    gy = torch.randn(*rows, o, generator=gen)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    torch.nn.functional.linear(xr, wr, br).backward(gy)
+    xm, wm, bm = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    y = ops.linear(xm, wm, bm)
+    y.backward(gy.to(DEV))
+    assert rel_l2(y.detach().cpu(), torch.nn.functional.linear(x, w, b)) < 1e-5
+    assert rel_l2(xm.grad.cpu(), xr.grad) < 1e-5 and rel_l2(wm.grad.cpu(), wr.grad) < 1e-5 and rel_l2(bm.grad.cpu(), br.grad) < 1e-5
