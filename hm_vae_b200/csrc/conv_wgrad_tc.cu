@@ -46,6 +46,7 @@ struct WgArgs {
   int a_bytes, b_bytes, stage_bytes, stages;
   int tmem_cols;
   int nitems;
+  int psplits, plen;     // position split: gridDim.y CTAs per item, each handles plen consecutive stages
   const WgItem* items;
 };
 
@@ -202,13 +203,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
   const int tg = item.k0 / p.Lmax;
+  const int nst_all = p.mtiles * p.nwin;
+  const int st_beg = blockIdx.y * p.plen;
+  const int st_end = (st_beg + p.plen < nst_all) ? st_beg + p.plen : nst_all;
+  if (p.psplits > 1) dw += (size_t)blockIdx.y * a.J * a.co * a.J * a.ci * a.K;      // this split's partial buffer
 
   if (warp == 0) {
     // =============================== producer ===============================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int mt = 0; mt < p.mtiles * p.nwin; ++mt) {
+      for (int mt = st_beg; mt < st_end; ++mt) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* st = smem_raw + (size_t)s * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p.a_bytes + p.b_bytes));
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
     int s = 0;
     uint32_t ph = 0;
-    for (int mt = 0; mt < p.mtiles * p.nwin; ++mt) {
+    for (int mt = st_beg; mt < st_end; ++mt) {
       mbar_wait(&full_bar[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
           uint64_t ad = adesc0;
           uint64_t bd = bdesc0 + (uint32_t)(phase * (p.Rx / 4) + shift * bq) * (uint32_t)p.n_pad;
           const uint32_t d_addr = tmem_base + (uint32_t)(t * p.n_pad);
-          uint32_t acc = (mt > 0) ? 1u : 0u;
+          uint32_t acc = (mt > st_beg) ? 1u : 0u;
 #pragma unroll 4
           for (int ks = 0; ks < ksteps; ++ks) {
             asm volatile(
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
             if (c < a.ci) {
               float* dst = wrow + (long)c * a.K + t;
               const float v = __uint_as_float(r[i]);
-              *dst = accumulate ? *dst + v : v;
+              *dst = (accumulate && p.psplits == 1) ? *dst + v : v;
             }
           }
         }
@@ -306,6 +311,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- split reduce
+// dw[e] (= or +=) sum over splits of part[s][e], for unmasked entries only, in a fixed order (deterministic)
+__global__ void conv_wgrad_reduce_kernel(WgArgs p, const float* __restrict__ part, float* __restrict__ dw, int accumulate) {
+  const ConvArgs& a = p.a;
+  const long per_row = (long)a.ci * a.K;
+  const long total = (long)a.nnz * a.co * per_row;
+  const long dense = (long)a.J * a.co * a.J * a.ci * a.K;
+  const int Cin = a.J * a.ci;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long x = e % per_row;
+    long r = e / per_row;
+    const int o = (int)(r % a.co);
+    const int blk = (int)(r / a.co);
+    const int j = a.blk_j[blk], n = a.blk_n[blk];
+    const long idx = ((long)(j * a.co + o) * Cin + n * a.ci) * a.K + x;
+    float v = 0.f;
+    for (int s2 = 0; s2 < p.psplits; ++s2) v += part[s2 * dense + idx];
+    dw[idx] = accumulate ? dw[idx] + v : v;
   }
 }
 
@@ -381,6 +407,16 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
     }
   }
   p.nitems = (int)items.size();
+  {
+    // split the (batch group, time window) stages over gridDim.y so that ~one wave of SMs is busy; >= 4 stages per CTA
+    const int nst = p.mtiles * p.nwin;
+    int splits = p.nitems > 0 ? num_sms() / p.nitems : 1;
+    if (splits > nst / 4) splits = nst / 4;
+    if (splits > 8) splits = 8;
+    if (splits < 1) splits = 1;
+    p.plen = (nst + splits - 1) / splits;
+    p.psplits = (nst + p.plen - 1) / p.plen;
+  }
   *out = p;
   *items_out = items;
   return p.nitems > 0;
@@ -420,6 +456,9 @@ static bool wg_geometry(const hmvae_conv_plan* plan, int B, int T, WgArgs* out) 
 
 static long wg_dy_bytes(const WgArgs& p) { return (long)p.mtiles * p.nwin * p.slabs * p.a_bytes; }
 static long wg_x_bytes(const WgArgs& p) { return (long)p.mtiles * p.nwin * p.a.J * p.TG * p.b_bytes; }
+static long wg_part_bytes(const WgArgs& p) {
+  return p.psplits > 1 ? (long)p.psplits * p.a.J * p.a.co * p.a.J * p.a.ci * p.a.K * 4 : 0;
+}
 
 bool conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int B, int T) {
   WgArgs p;
@@ -429,7 +468,7 @@ bool conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int B, int T) {
 long conv_wgrad_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T) {
   WgArgs p;
   if (!wg_geometry(plan, B, T, &p)) return -1;
-  return wg_dy_bytes(p) + wg_x_bytes(p);
+  return wg_dy_bytes(p) + wg_x_bytes(p) + wg_part_bytes(p);
 }
 
 int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* yact, float* dw,
@@ -437,7 +476,7 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
                          cudaStream_t st) {
   WgArgs p;
   if (!wg_geometry(plan, B, T, &p)) return fail_arg("conv_wgrad (tcgen05): unsupported geometry");
-  if (!workspace || workspace_bytes < wg_dy_bytes(p) + wg_x_bytes(p) || !aligned16(workspace))
+  if (!workspace || workspace_bytes < wg_dy_bytes(p) + wg_x_bytes(p) + wg_part_bytes(p) || !aligned16(workspace))
     return fail_arg("conv_wgrad (tcgen05): workspace too small or misaligned");
   unsigned char* dyw = reinterpret_cast<unsigned char*>(workspace);
   unsigned char* xw = dyw + wg_dy_bytes(p);
@@ -457,8 +496,15 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   HMVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv_wgrad_tc_kernel<<<p.nitems, WG_THREADS, smem, st>>>(p, dyw, xw, dw, accumulate);
-  return check_launch("conv_wgrad_tc");
+  float* part = reinterpret_cast<float*>(xw + wg_x_bytes(p));
+  dim3 grid(p.nitems, p.psplits);
+  conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(p, dyw, xw, p.psplits > 1 ? part : dw, accumulate);
+  int rc = check_launch("conv_wgrad_tc");
+  if (rc || p.psplits <= 1) return rc;
+  const long total = (long)p.a.nnz * p.a.co * p.a.ci * p.a.K;
+  long blocks = (total + 255) / 256, cap = (long)num_sms() * 8;
+  conv_wgrad_reduce_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, part, dw, accumulate);
+  return check_launch("conv_wgrad_reduce");
 }
 
 }  // namespace hmvae
