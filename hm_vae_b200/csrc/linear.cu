@@ -5,56 +5,79 @@
 
 namespace hmvae {
 
-// y[r, o] = sum_i x[r, i] * w[o, i] + bias[o].  The whole weight (<= 96 KB) and RB rows of x are staged in shared memory with all
-// loads in flight at once (these GEMMs are latency-, not throughput-bound); odd pitch => conflict-free.
-constexpr int LIN_RB = 8;
+// ---- y[r, o] = sum_i x[r, i] * w[o, i] + bias[o]      (both operands contiguous along the reduction)
+// One warp per (row, 8 outputs): lanes stride over i (128-byte coalesced loads), 8 accumulators, warp reductions.
+constexpr int NT_OB = 8;
 __global__ void __launch_bounds__(256) linear_nt_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y, int R, int I,
                                                         int O) {
-  extern __shared__ float sm[];
-  const int pitch = I | 1;
-  float* ws = sm;                    // [O][pitch]
-  float* xs = sm + (size_t)O * pitch;   // [RB][I]
-  const int r0 = blockIdx.x * LIN_RB;
-  for (int e = threadIdx.x; e < O * I; e += 256) ws[(e / I) * pitch + e % I] = w[e];
-  for (int e = threadIdx.x; e < LIN_RB * I; e += 256) {
-    const int r = r0 + e / I;
-    xs[e] = r < R ? x[(long)r * I + e % I] : 0.f;
+  const int lane = threadIdx.x & 31;
+  const int ogroups = (O + NT_OB - 1) / NT_OB;
+  const long wid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wid >= (long)R * ogroups) return;
+  const int r = (int)(wid / ogroups), o0 = (int)(wid % ogroups) * NT_OB;
+  const float* xr = x + (long)r * I;
+  float acc[NT_OB];
+#pragma unroll
+  for (int u = 0; u < NT_OB; ++u) acc[u] = 0.f;
+  for (int i = lane; i < I; i += 32) {
+    const float xv = xr[i];
+#pragma unroll
+    for (int u = 0; u < NT_OB; ++u)
+      if (o0 + u < O) acc[u] += xv * w[(long)(o0 + u) * I + i];
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < LIN_RB * O; e += 256) {
-    const int rl = e / O, o = e % O;
-    if (r0 + rl >= R) continue;
-    const float* xr = xs + rl * I;
-    const float* wr = ws + o * pitch;
-    float acc0 = 0.f, acc1 = 0.f;
-    int i = 0;
-    for (; i + 1 < I; i += 2) { acc0 += xr[i] * wr[i]; acc1 += xr[i + 1] * wr[i + 1]; }
-    if (i < I) acc0 += xr[i] * wr[i];
-    y[(long)(r0 + rl) * O + o] = acc0 + acc1 + (bias ? bias[o] : 0.f);
+#pragma unroll
+  for (int u = 0; u < NT_OB; ++u) {
+    const float v = warp_sum(acc[u]);
+    if (lane == 0 && o0 + u < O) y[(long)r * O + o0 + u] = v + (bias ? bias[o0 + u] : 0.f);
   }
 }
 
-// C[m, n] = sum_k A(m, k) * B(k, n),  A(m,k) = a[m*am + k*ak], B(k,n) = b[k*bk + n*bn], C row-major [M, N].
-// One thread per output; the caller picks which of (m, n) runs fastest across threads so that the big operand is read
-// coalesced and the other one is a warp broadcast.  Independent loads, unrolled => high memory-level parallelism.
-__global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict__ a, long am, long ak,
-                                                         const float* __restrict__ b, long bk, long bn, float* __restrict__ c,
-                                                         int M, int N, int K, int n_fastest) {
+// ---- dx[r, i] = sum_o dy[r, o] * w[o, i]      (short reduction, wide contiguous output): one thread per output
+__global__ void __launch_bounds__(256) linear_nn_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                        float* __restrict__ dx, int R, int I, int O) {
   const long e = (long)blockIdx.x * 256 + threadIdx.x;
-  if (e >= (long)M * N) return;
-  const int m = n_fastest ? (int)(e / N) : (int)(e % M);
-  const int n = n_fastest ? (int)(e % N) : (int)(e / M);
-  const float* ap = a + m * am;
-  const float* bp = b + n * bn;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int k = 0;
-  for (; k + 3 < K; k += 4) {
+  if (e >= (long)R * I) return;
+  const int r = (int)(e / I), i = (int)(e % I);
+  const float* g = dy + (long)r * O;
+  float acc0 = 0.f, acc1 = 0.f;
+  int o = 0;
+  for (; o + 1 < O; o += 2) { acc0 += g[o] * w[(long)o * I + i]; acc1 += g[o + 1] * w[(long)(o + 1) * I + i]; }
+  if (o < O) acc0 += g[o] * w[(long)o * I + i];
+  dx[e] = acc0 + acc1;
+}
+
+// ---- C[a, b] = sum_r P[r, a] * Q[r, b]      (long reduction over rows; Q wide, P narrow)
+// CTA = 8 a x 32 b outputs; the 8 warps split the rows, partial sums are combined through shared memory in a fixed order.
+// out index = transpose ? b*A + a : a*Bn + b.
+__global__ void __launch_bounds__(256) linear_tn_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                                                        float* __restrict__ out, int R, int A, int Bn, int transpose) {
+  __shared__ float red[8][8][33];
+  const int lane = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane, a0 = blockIdx.y * 8;
+  float acc[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] += ap[(k + u) * ak] * bp[(k + u) * bk];
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  if (b < Bn) {
+    for (int r = ks; r < R; r += 8) {
+      const float q = Q[(long)r * Bn + b];
+      const float* pr = P + (long)r * A + a0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (a0 + u < A) acc[u] += pr[u] * q;
+    }
   }
-  for (; k < K; ++k) acc[0] += ap[k * ak] * bp[k * bk];
-  c[(long)m * N + n] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[ks][u][lane] = acc[u];
+  __syncthreads();
+  // thread (ks = u, lane) finalises output (a0 + u, b)
+  const int u = ks;
+  if (b < Bn && a0 + u < A) {
+    float v = 0.f;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) v += red[k2][u][lane];
+    out[transpose ? (long)b * A + a0 + u : (long)(a0 + u) * Bn + b] = v;
+  }
 }
 
 // out[n] = sum_m x[m, n]   (x row-major [M, N]); one warp per 32 columns chunk, fixed order
@@ -75,13 +98,6 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
-static int gemm(const float* a, long am, long ak, const float* b, long bk, long bn, float* c, int M, int N, int K, int n_fastest,
-                cudaStream_t st, const char* what) {
-  const long total = (long)M * N;
-  small_gemm_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(a, am, ak, b, bk, bn, c, M, N, K, n_fastest);
-  return check_launch(what);
-}
-
 }  // namespace hmvae
 
 using namespace hmvae;
@@ -90,10 +106,8 @@ extern "C" int hmvae_linear_fwd(const float* x, const float* w, const float* bia
                                 void* stream) {
   if (!x || !w || !y) return fail_arg("linear_fwd: null pointer");
   if (rows <= 0 || in_f <= 0 || out_f <= 0) return 0;
-  const size_t smem = ((size_t)out_f * (in_f | 1) + (size_t)LIN_RB * in_f) * 4;
-  if (smem > 200 * 1024) return fail_arg("linear_fwd: weight does not fit shared memory (latent heads only)");
-  if (smem > 48 * 1024) HMVAE_CUDA(cudaFuncSetAttribute(linear_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  linear_nt_kernel<<<(rows + LIN_RB - 1) / LIN_RB, 256, smem, (cudaStream_t)stream>>>(x, w, bias, y, rows, in_f, out_f);
+  const long warps = (long)rows * ((out_f + NT_OB - 1) / NT_OB);
+  linear_nt_kernel<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, rows, in_f, out_f);
   return check_launch("linear_fwd");
 }
 
@@ -102,14 +116,28 @@ extern "C" int hmvae_linear_bwd(const float* x, const float* w, const float* dy,
   if (!dy || (dx && !w) || (dw && !x)) return fail_arg("linear_bwd: null pointer");
   if (rows <= 0 || in_f <= 0 || out_f <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = 0;
-  // dx[r,i] = sum_o dy[r,o] w[o,i]   : threads run over i (w coalesced, dy broadcast)
-  if (dx) rc = gemm(dy, out_f, 1, w, in_f, 1, dx, rows, in_f, out_f, 1, st, "linear_bwd(dx)");
-  // dw[o,i] = sum_r dy[r,o] x[r,i]   : threads run over the wider of (o, i) so that the wider operand is read coalesced
-  if (!rc && dw) rc = gemm(dy, 1, out_f, x, in_f, 1, dw, out_f, in_f, rows, in_f >= out_f ? 1 : 0, st, "linear_bwd(dw)");
-  if (!rc && db) {
-    colsum_kernel<<<(out_f + 31) / 32, 256, 0, st>>>(dy, db, rows, out_f);
-    rc = check_launch("linear_bwd(db)");
+  if (dx) {
+    const long total = (long)rows * in_f;
+    linear_nn_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(dy, w, dx, rows, in_f, out_f);
+    int rc = check_launch("linear_bwd(dx)");
+    if (rc) return rc;
   }
-  return rc;
+  if (dw) {
+    // dw[o, i] = sum_r dy[r, o] x[r, i]: the wider of the two operands is read coalesced
+    if (in_f >= out_f) {
+      dim3 grid((in_f + 31) / 32, (out_f + 7) / 8);
+      linear_tn_kernel<<<grid, 256, 0, st>>>(dy, x, dw, rows, out_f, in_f, 0);
+    } else {
+      dim3 grid((out_f + 31) / 32, (in_f + 7) / 8);
+      linear_tn_kernel<<<grid, 256, 0, st>>>(x, dy, dw, rows, in_f, out_f, 1);
+    }
+    int rc = check_launch("linear_bwd(dw)");
+    if (rc) return rc;
+  }
+  if (db) {
+    colsum_kernel<<<(out_f + 31) / 32, 256, 0, st>>>(dy, db, rows, out_f);
+    int rc = check_launch("linear_bwd(db)");
+    if (rc) return rc;
+  }
+  return 0;
 }

@@ -97,6 +97,9 @@ class BucketedAllReduce:
                 dist.all_reduce(g, group=self.group)
             return
         self.comm_stream.wait_stream(torch.cuda.current_stream())
+        from . import ops
+        if ops._overlap["side"] is not None and ops._overlap["pending"]:
+            self.comm_stream.wait_stream(ops._overlap["side"])       # weight gradients are produced on the side stream
         with torch.cuda.stream(self.comm_stream):
             with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
                 for g in grads:

@@ -3,6 +3,7 @@
 Every op here launches hand-written sm_100a kernels from libhmvae_b200.so on the current CUDA stream, on
 caller-owned fp32 tensors; outputs come from PyTorch's caching allocator.  There is no CPU path.
 """
+import contextlib
 import ctypes
 
 import torch
@@ -62,6 +63,33 @@ class ConvPlan:
 
 
 _force_repack = False
+_overlap = {"on": False, "side": None, "pending": []}
+
+
+def _side_stream():
+    if _overlap["side"] is None:
+        _overlap["side"] = torch.cuda.Stream()
+    return _overlap["side"]
+
+
+def join_wgrad():
+    """Makes the current stream wait for the weight gradients issued on the side stream."""
+    if _overlap["pending"]:
+        torch.cuda.current_stream().wait_stream(_overlap["side"])
+        _overlap["pending"].clear()
+
+
+class wgrad_overlap:
+    """Context manager: conv weight gradients of backward passes run inside it go to a side stream; joined on exit."""
+
+    def __enter__(self):
+        _overlap["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _overlap["on"] = False
+        join_wgrad()
+        return False
 _wgrad_tc = True          # tensor-core weight gradient where the geometry is supported (False: CUDA-core wgrad)
 
 
@@ -155,17 +183,27 @@ class _SkeletonConvFn(Function):
             else:
                 gx = gxin
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gb = torch.empty(plan.joints * plan.co, device=x.device, dtype=torch.float32) if ctx.has_bias else None
-            if _wgrad_tc and _conv_impl != IMPL_SIMT and lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in):
-                gw = torch.zeros_like(w)                  # masked blocks are never written: they must read 0
-                n = int(lib.hmvae_conv_wgrad_tc_workspace(plan.handle, b, t_in))
-                ws = torch.empty((n + 3) // 4, device=x.device, dtype=torch.float32)
-                check(lib.hmvae_conv_wgrad_tc(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, ptr(ws), ws.numel() * 4,
-                                              stream()), "conv_wgrad_tc")
-            else:
-                gw = torch.empty_like(w)
-                check(lib.hmvae_conv_wgrad(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, _conv_impl, stream()),
-                      "conv_wgrad")
+            # the weight gradient does not feed the rest of the backward pass: inside ``wgrad_overlap()`` it is issued on a side
+            # stream so that it runs under the following layers' dgrad (most grids here are smaller than the 148 SMs)
+            side = None
+            if _overlap["on"]:
+                side = _side_stream()
+                side.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                gb = torch.empty(plan.joints * plan.co, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+                ws = None
+                if _wgrad_tc and _conv_impl != IMPL_SIMT and lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in):
+                    gw = torch.zeros_like(w)                  # masked blocks are never written: they must read 0
+                    n = int(lib.hmvae_conv_wgrad_tc_workspace(plan.handle, b, t_in))
+                    ws = torch.empty((n + 3) // 4, device=x.device, dtype=torch.float32)
+                    check(lib.hmvae_conv_wgrad_tc(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, ptr(ws),
+                                                  ws.numel() * 4, stream()), "conv_wgrad_tc")
+                else:
+                    gw = torch.empty_like(w)
+                    check(lib.hmvae_conv_wgrad(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, _conv_impl, stream()),
+                          "conv_wgrad")
+            if side is not None:
+                _overlap["pending"].extend([x, gy, y, gw, gb, ws])       # keep every buffer alive until the join
         return gx, gw, gb, None
 
 

@@ -300,7 +300,8 @@ class TwoHierSAVAEModel(nn.Module):
         l_total, l_kl = res[6], res[7]
 
         if not validation_flag:
-            out.backward(dx6)
+            with ops.wgrad_overlap():
+                out.backward(dx6)
 
         return l_total, l_kl, l_rec_6d, l_rec_rot_mat, l_rec_pose, zero, zero, zero, zero, l_kl_list
 

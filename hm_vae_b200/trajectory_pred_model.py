@@ -116,7 +116,8 @@ class TrajectoryModel(nn.Module):
             l_rec_root_trans = torch.zeros(1, device=dev)
         l_total = hp['rec_root_v_w'] * l_rec_root_v + hp['rec_root_trans_w'] * l_rec_root_trans
         if not validation_flag:
-            root_v_out.backward(d_root_v)
+            with ops.wgrad_overlap():
+                root_v_out.backward(d_root_v)
         zero = torch.zeros(1, device=dev)
         return l_total, zero, zero, zero, zero, zero, l_rec_root_v, zero, l_rec_root_trans
 
