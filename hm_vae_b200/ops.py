@@ -203,7 +203,9 @@ class _SkeletonConvFn(Function):
                     check(lib.hmvae_conv_wgrad(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, _conv_impl, stream()),
                           "conv_wgrad")
             if side is not None:
-                _overlap["pending"].extend([x, gy, y, gw, gb, ws])       # keep every buffer alive until the join
+                # keep the INPUT buffers alive until the join.  gw / gb must NOT be referenced here: AccumulateGrad only steals a
+                # gradient it holds the sole reference to -- otherwise it clones it on the main stream, before the side stream wrote it
+                _overlap["pending"].extend([x, gy, y, ws])
         return gx, gw, gb, None
 
 
