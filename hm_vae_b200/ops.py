@@ -103,18 +103,50 @@ class PackedWeights:
         self.plan, self.nf, self.nd = plan, nf.value, nd.value
         self.wp_f = self.wp_d = None
         self.key = None
+        self.event = None
 
-    def get(self, weight):
-        key = (weight._version, weight.data_ptr())
+    def _ensure(self, weight):
         if self.wp_f is None or self.wp_f.device != weight.device:
             self.wp_f = torch.zeros(self.nf, device=weight.device, dtype=torch.float32)   # padding stays zero forever
             self.wp_d = torch.zeros(self.nd, device=weight.device, dtype=torch.float32)
             self.key = None
-        if key != self.key or _force_repack:
-            check(lib.hmvae_conv_pack_weights(self.plan.handle, ptr(weight.detach()), ptr(self.wp_f), ptr(self.wp_d), stream()),
-                  "conv_pack_weights")
-            self.key = key
+            self.event = None
+
+    def _pack(self, weight):
+        check(lib.hmvae_conv_pack_weights(self.plan.handle, ptr(weight.detach()), ptr(self.wp_f), ptr(self.wp_d), stream()),
+              "conv_pack_weights")
+        self.key = (weight._version, weight.data_ptr())
+
+    def prefetch(self, weight):
+        """Re-packs on the CURRENT (side) stream if the weight changed and records an event that ``get`` waits for."""
+        self._ensure(weight)
+        if (weight._version, weight.data_ptr()) != self.key or _force_repack:
+            self._pack(weight)
+            self.event = torch.cuda.Event()
+            self.event.record()
+
+    def get(self, weight):
+        self._ensure(weight)
+        if (weight._version, weight.data_ptr()) != self.key or (_force_repack and self.event is None):
+            self._pack(weight)
+        if self.event is not None:                      # packed on the side stream by prefetch()
+            torch.cuda.current_stream().wait_event(self.event)
+            self.event = None
         return self.wp_f, self.wp_d
+
+
+def prefetch_packs(items):
+    """items: [(plan, weight)] in forward order.  Re-packs every changed conv weight on the side stream, so that the packing of
+    layer i+1.. runs under the forward pass of layers ..i; each conv waits only for its own event."""
+    if _conv_impl == IMPL_SIMT or not items:
+        return
+    side = _side_stream()
+    side.wait_stream(torch.cuda.current_stream())         # after the optimiser update / the previous step's readers
+    with torch.cuda.stream(side):
+        for plan, weight in items:
+            if not hasattr(plan, "packed"):
+                plan.packed = PackedWeights(plan)
+            plan.packed.prefetch(weight.contiguous())
 
 
 def _workspace(plan, b, t_in, mode, device):
@@ -424,10 +456,21 @@ class _LinearFn(Function):
         x2, w = ctx.saved_tensors
         rows, in_f, out_f = x2.shape[0], x2.shape[1], w.shape[0]
         gy2 = gy.reshape(rows, out_f).contiguous()
-        gx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
-        gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
-        gb = torch.empty(out_f, device=w.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        check(lib.hmvae_linear_bwd(ptr(x2), ptr(w), ptr(gy2), ptr(gx), ptr(gw), ptr(gb), rows, in_f, out_f, stream()), "linear_bwd")
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x2)
+            check(lib.hmvae_linear_bwd(ptr(x2), ptr(w), ptr(gy2), ptr(gx), None, None, rows, in_f, out_f, stream()), "linear_bwd(dx)")
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            side = None
+            if _overlap["on"]:
+                side = _side_stream()
+                side.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+                gb = torch.empty(out_f, device=w.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+                check(lib.hmvae_linear_bwd(ptr(x2), ptr(w), ptr(gy2), None, ptr(gw), ptr(gb), rows, in_f, out_f, stream()), "linear_bwd(dw)")
+            if side is not None:
+                _overlap["pending"].extend([x2, gy2])
         return (gx.view(ctx.shape) if gx is not None else None), gw, gb
 
 

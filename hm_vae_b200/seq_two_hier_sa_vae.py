@@ -86,12 +86,19 @@ class Encoder(nn.Module):
             self.pooling_list.append(pool.pooling_list)
             self.edge_num.append(len(self.topologies[-1]))
 
+    def _identity_pool(self, i):
+        return all(len(p) == 1 and p[0] == k for k, p in enumerate(self.pools[i].pooling_list))
+
+    def conv_plans(self):
+        """[(plan, weight)] of the main convs in forward order (for ops.prefetch_packs)."""
+        return [(c.plan(lrelu=True) if self._identity_pool(i) else c.plan(), c.weight) for i, c in enumerate(self.convs)]
+
     def _level(self, i, x):
         seq = self.layers[i]
         for m in list(seq)[:-3]:              # extra convs (none in the shipped configs)
             x = m(x)
         conv, pool = self.convs[i], self.pools[i]
-        if all(len(p) == 1 and p[0] == k for k, p in enumerate(pool.pooling_list)):
+        if self._identity_pool(i):
             return conv.fused_forward(x, lrelu=True)          # identity pool (last level): conv + LeakyReLU epilogue
         return pool(conv(x), lrelu=True)                       # pool + LeakyReLU in one kernel
 
@@ -163,6 +170,16 @@ class Decoder(nn.Module):
         if args.get('upsampling', 'linear') != 'linear':
             raise NotImplementedError("only upsampling='linear' (all shipped configs) is built")
 
+    def _fused_kwargs(self, i):
+        unpool = self.unpools[i]
+        return dict(upsample=self.upsample[i], unpool_src=unpool.src, src_joints=unpool.input_edge_num,
+                    lrelu=(i != self.hp['num_layers'] - 1))
+
+    def conv_plans(self):
+        if self.hp['extra_conv']:
+            return []
+        return [(c.plan(**self._fused_kwargs(i)), c.weight) for i, c in enumerate(self.convs)]
+
     def _level(self, i, x):
         n = self.hp['num_layers']
         conv, unpool = self.convs[i], self.unpools[i]
@@ -175,8 +192,7 @@ class Decoder(nn.Module):
                 if isinstance(m, SkeletonConv) and m is not conv:
                     x = m(x)
             return conv.fused_forward(x, lrelu=(i != n - 1))
-        return conv.fused_forward(x, upsample=self.upsample[i], unpool_src=unpool.src, src_joints=unpool.input_edge_num,
-                                  lrelu=(i != n - 1))
+        return conv.fused_forward(x, **self._fused_kwargs(i))
 
     def forward(self, z_vec_list, offset=None):
         """z_vec_list: shallow -> deep, each [B, k_edges, latent]; entries 1..n-2 may be None (they are dead inputs)."""
@@ -261,6 +277,7 @@ class TwoHierSAVAEModel(nn.Module):
         n = hp['num_layers']
         detach_shallow = iterations < hp['iteration_interval']
 
+        ops.prefetch_packs(self.enc.conv_plans() + self.dec.conv_plans())   # tf32 weight copies, on the side stream
         x = ops.transpose_ct(seq_rot_6d)                            # bs X (24*6) X T   (input is [B, T, C])
         _, z_vec_list = self.enc(x, needed={0, n - 1})
         k_edges = [len(p) for p in self.enc.pooling_list]
