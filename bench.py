@@ -319,9 +319,12 @@ def run_b200(args, hp):
     prof_steps = 5
     with KernelTimer(_lib.lib) as kt:
         saved, trainer._graphs = trainer._graphs, {}
+        sync_was = trainer._sync.enabled
+        trainer._sync.enabled = True
         for _ in range(prof_steps):
             trainer.gen_update(data, hp, iters0)
         trainer._graphs = saved
+        trainer._sync.enabled = sync_was
     barrier()
     line = None
     if rank == 0:
@@ -368,6 +371,8 @@ def run_b200(args, hp):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(600, exit=True)      # a hung collective prints where every thread is and exits
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -76,12 +76,27 @@ class BucketedAllReduce:
                 if self.world > 1:
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self.launched = 0
+        self.enabled = True       # False: hooks are inert (used while a CUDA graph of fwd+bwd is captured / replayed)
+
+    def allreduce_now(self):
+        """All buckets, in backward order, on the current stream (no overlap): the step's fwd+bwd ran as a CUDA graph."""
+        if self.world <= 1:
+            return
+        for bucket in self.buckets:
+            grads = [p.grad for _, p in bucket if p.grad is not None]
+            if not grads:
+                continue
+            with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
+                for g in grads:
+                    dist.all_reduce(g, group=self.group)
 
     def begin(self):
         self._pending = [len(b) for b in self.buckets]
         self.launched = 0
 
     def _on_grad(self, p):
+        if not self.enabled:
+            return
         bi = self._bucket_of[id(p)]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
@@ -109,7 +124,7 @@ class BucketedAllReduce:
 
     def finish(self):
         """Flushes buckets whose hooks did not all fire (unused parameters) and joins the comm stream."""
-        if self.world <= 1:
+        if self.world <= 1 or not self.enabled:
             return
         for bi, left in enumerate(self._pending):
             if left > 0:

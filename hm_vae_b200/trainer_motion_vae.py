@@ -95,6 +95,11 @@ class Trainer(nn.Module):
         self.gen_opt.step_dyn(grad_scale=1.0 / self._sync.world)
         return out
 
+    def _fwd_bwd(self, data, hp, iterations):
+        """forward + backward only, no collective (the part that is captured as a CUDA graph when world > 1)."""
+        self.gen_opt.zero_grad(set_to_none=True)
+        return self.model(data, hp, iterations)
+
     def _record(self, out, validation):
         names = ["total", "kl", "rec_6d", "rec_rot", "rec_pose", "rec_joint_pos", "rec_root_v", "rec_linear_v", "rec_angular_v"]
         prefix = "loss_val_" if validation else "loss_"
@@ -125,6 +130,10 @@ class Trainer(nn.Module):
                     dst.copy_(src, non_blocking=True)
             graph.replay()
             out = static_out
+            if self._sync.world > 1:
+                # multi-GPU: the graph holds forward+backward; the NCCL all-reduce and the Adam kernel follow eagerly
+                self._sync.allreduce_now()
+                self.gen_opt.step_dyn(grad_scale=1.0 / self._sync.world)
         else:
             out = self._device_step(data, hp, iterations)
         return self._record(out, False)
@@ -142,6 +151,7 @@ class Trainer(nn.Module):
         self._ensure_opt()
         dev = next(self.model.parameters()).device
         static_in = [d.to(device=dev, dtype=torch.float32).clone() if torch.is_tensor(d) else None for d in data]
+        multi = self._sync.world > 1
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -154,11 +164,15 @@ class Trainer(nn.Module):
         graph = torch.cuda.CUDAGraph()
         n0 = ops._lib.launch_count()
         ops._force_repack = True            # the packed tf32 weight copies must be refreshed inside every replay
+        self._sync.enabled = not multi      # no NCCL inside the graph: with world > 1 only forward+backward is captured
         try:
             with torch.cuda.graph(graph):
-                static_out = self._device_step(static_in, hp, iterations)
+                static_out = self._fwd_bwd(static_in, hp, iterations) if multi else self._device_step(static_in, hp, iterations)
         finally:
             ops._force_repack = False
+        if multi:
+            # the capture pass itself executed nothing: leave the hooks off for good (eager all-reduce after each replay)
+            self._sync.enabled = False
         self.launches_per_step = ops._lib.launch_count() - n0
         self._graphs[self._graph_key(hp, iterations, data)] = (graph, static_in, static_out)
         return graph
