@@ -123,10 +123,14 @@ def run_reference(args, hp):
 class KernelTimer:
     """Wraps the C-ABI entry points with CUDA events (on the launching stream) to attribute step time to kernels."""
 
-    CONV = ("hmvae_conv_fprop", "hmvae_conv_dgrad", "hmvae_conv_wgrad")
+    CONV = {"fprop": ("hmvae_conv_fprop", "hmvae_conv_fprop_tc"), "dgrad": ("hmvae_conv_dgrad", "hmvae_conv_dgrad_tc"),
+            "wgrad": ("hmvae_conv_wgrad", "hmvae_conv_wgrad_tc")}
 
-    def __init__(self, lib):
-        self.lib, self.records, self.orig = lib, [], {}
+    def __init__(self, lib, repeat=1):
+        """repeat > 1: every conv compute entry point is issued `repeat` times back to back between its two events (the
+        calls are idempotent), so that the launch queue is full and the event pair measures device time, not host gaps."""
+        self.lib, self.records, self.orig, self.repeat = lib, [], {}, repeat
+        self.conv_names = {n for v in self.CONV.values() for n in v}
 
     def __enter__(self):
         from hm_vae_b200 import _lib
@@ -140,12 +144,15 @@ class KernelTimer:
         return self
 
     def _wrap(self, name, fn):
+        rep = self.repeat if name in self.conv_names else 1
+
         def call(*a):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            rc = fn(*a)
+            for _ in range(rep):
+                rc = fn(*a)
             e1.record()
-            self.records.append((name, a, e0, e1))
+            self.records.append((name, a, e0, e1, rep))
             return rc
         return call
 
@@ -156,9 +163,9 @@ class KernelTimer:
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, a, e0, e1 in self.records:
+        for name, a, e0, e1, rep in self.records:
             d = out.setdefault(name, dict(ms=0.0, calls=0))
-            d["ms"] += e0.elapsed_time(e1)
+            d["ms"] += e0.elapsed_time(e1) / rep
             d["calls"] += 1
         return out
 
@@ -166,30 +173,68 @@ class KernelTimer:
         """conv time per (entry point, layer); layers are labelled by the order their plans first appear in a step."""
         torch.cuda.synchronize()
         order, out = {}, {}
-        for name, a, e0, e1 in self.records:
+        for name, a, e0, e1, rep in self.records:
             if not name.startswith("hmvae_conv_") or name in ("hmvae_conv_tc_supported", "hmvae_conv_tc_workspace", "hmvae_conv_packed_size"):
                 continue
             key = a[0].value if hasattr(a[0], "value") else a[0]
             idx = order.setdefault(key, len(order))
             k = "%s[L%d]" % (name.replace("hmvae_conv_", ""), idx)
-            out[k] = out.get(k, 0.0) + e0.elapsed_time(e1) / steps
+            out[k] = out.get(k, 0.0) + e0.elapsed_time(e1) / rep / steps
         return {k: round(v * 1e3, 1) for k, v in sorted(out.items())}
 
 
-def conv_flops_per_step(model, batch):
-    """Algorithmic FLOPs of the unmasked blocks only: 2*B*T_out*K*co*ci*nnz per conv, fwd; x3 for fwd+bwd."""
-    total = 0
-    t = model.max_timesteps
+def conv_flops(model, batch, enc_passes=1, dec_passes=1):
+    """Algorithmic FLOPs of the unmasked blocks only: 2*B*T_out*K*co*ci*nnz per conv, forward."""
+    enc = dec = 0
     ts = model.enc.timestep_list
     for i, conv in enumerate(model.enc.convs):
         nnz = sum(len(nb) for nb in conv.neighbour_list)
-        total += 2 * batch * ts[i + 1] * conv.kernel_size * conv.out_channels_per_joint * conv.in_channels_per_joint * nnz
+        enc += 2 * batch * ts[i + 1] * conv.kernel_size * conv.out_channels_per_joint * conv.in_channels_per_joint * nnz
     dts = model.dec.timestep_list
     for i, conv in enumerate(model.dec.convs):
         t_out = dts[i] * (2 if model.dec.upsample[i] else 1)
         nnz = sum(len(nb) for nb in conv.neighbour_list)
-        total += 2 * batch * t_out * conv.kernel_size * conv.out_channels_per_joint * conv.in_channels_per_joint * nnz
-    return total
+        dec += 2 * batch * t_out * conv.kernel_size * conv.out_channels_per_joint * conv.in_channels_per_joint * nnz
+    return enc_passes * enc + dec_passes * dec
+
+
+def conv_flops_per_step(model, batch):
+    return conv_flops(model, batch)
+
+
+def inference_leg(model, hp, dev, pk, batch=512, iters=10):
+    """BASELINE config 4: len64 `test()` path at B=512 (1 encoder + 2 decoder passes + 2 rot6d + 3 FK, no grad) -- the
+    regime where the conv kernels have enough rows to be tensor-pipe bound.  Reports sequences/s and the conv TFLOP/s
+    (algorithmic FLOPs of 1 enc + 2 dec passes / device time spent inside the conv entry points)."""
+    from hm_vae_b200 import _lib
+
+    T = hp["train_seq_len"]
+    d6, dm = synthetic_device_batch(batch, T, dev, 99)
+    g = torch.Generator().manual_seed(5)
+    ks = [len(p) for p in model.enc.pooling_list]
+    lat = [model.shallow_latent_d] + [model.latent_d] * (len(ks) - 1)
+    zs = [torch.randn(batch, k, d, generator=g).to(dev) for k, d in zip(ks, lat)]
+    for _ in range(3):
+        model.test((d6, dm), hp, 0, sampled_z_list=zs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        model.test((d6, dm), hp, 0, sampled_z_list=zs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    with KernelTimer(_lib.lib, repeat=4) as kt:
+        for _ in range(2):
+            model.test((d6, dm), hp, 0, sampled_z_list=zs)
+    summ = kt.summary()
+    conv_ms = sum(summ.get(n, dict(ms=0.0))["ms"] for n in KernelTimer.CONV["fprop"]) / 2
+    fl = conv_flops(model, batch, enc_passes=1, dec_passes=2)
+    tf = fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+    return {"workload": "configs/len_64_test_interpolation.yaml test() path, B=%d, no grad, eager" % batch, "ms_per_call": ms,
+            "sequences_per_s": batch / (ms * 1e-3), "conv_fprop_ms": conv_ms, "conv_algorithmic_gflop": fl / 1e9,
+            "conv_tflops": tf, "conv_frac_of_tf32_peak": (tf / (pk["bf16"] / 2.0)) if tf else None,
+            "conv_us_per_layer": kt.per_layer(2)}
 
 
 # ------------------------------------------------------------------------------------------------ main arm
@@ -205,39 +250,53 @@ def synthetic_device_batch(bs, t, dev, seed):
     return seq_rot_6d, seq_rot_mat
 
 
-def fk_sweep(dev, pk, frames=699051, iters=10):
-    """BASELINE config 3 at its largest size: FK fwd and bwd, achieved algorithmic GB/s."""
-    import hm_vae_b200 as H
+def fk_sweep(dev, pk, sizes=(10923, 174763, 699051), iters=20):
+    """BASELINE config 3: FK and rot6d->R, fwd and bwd kernels timed through the C ABI (no autograd glue), achieved
+    algorithmic GB/s (FK 48 / 84 B per joint-frame, rot6d 60 / 84).  The largest size is the headline."""
+    from hm_vae_b200 import _lib
+    from hm_vae_b200._lib import check, int_array, lib, ptr, stream
+    from hm_vae_b200.fk_layer import load_smpl24
 
-    fk = H.ForwardKinematicsLayer(device=dev)
+    parents, offsets, _ = load_smpl24()
+    par = int_array(parents)
+    off = torch.as_tensor(offsets, dtype=torch.float32, device=dev).contiguous()
     g = torch.Generator().manual_seed(1)
-    rot = H.rotation_matrix_from_ortho6d(torch.randn(frames, 24, 6, generator=g).to(dev)).requires_grad_(True)
-    gp = torch.randn(frames, 24, 3, generator=g).to(dev)
-    res = {}
-    for _ in range(3):
-        pos = fk(rot)
-        pos.backward(gp)
-        rot.grad = None
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    tf = tb = 0.0
-    for _ in range(iters):
-        e[0].record()
-        pos = fk(rot)
-        e[1].record()
-        pos.backward(gp)
-        e[2].record()
+    out = {"sizes": {}}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
         torch.cuda.synchronize()
-        tf += e[0].elapsed_time(e[1])
-        tb += e[1].elapsed_time(e[2])
-        rot.grad = None
-    jf = frames * 24
-    res["frames"] = frames
-    res["fwd_gbs"] = 48.0 * jf / (tf / iters * 1e-3) / 1e9
-    res["bwd_gbs"] = 84.0 * jf / (tb / iters * 1e-3) / 1e9
-    res["fwd_frac"] = res["fwd_gbs"] / pk["hbm"]
-    res["bwd_frac"] = res["bwd_gbs"] / pk["hbm"]
-    res["note"] = "algorithmic bytes 48 B/jf fwd, 84 B/jf bwd (bwd time includes autograd glue); inputs 604 MB > L2"
-    return res
+        return e0.elapsed_time(e1) / iters * 1e-3
+
+    for frames in sizes:
+        x6 = torch.randn(frames, 24, 6, generator=g).to(dev)
+        rot = torch.empty(frames, 24, 3, 3, device=dev)
+        check(lib.hmvae_rot6d_fwd(ptr(x6), ptr(rot), frames * 24, stream()), "rot6d_fwd")
+        gp = torch.randn(frames, 24, 3, generator=g).to(dev)
+        gr = torch.randn(frames, 24, 3, 3, generator=g).to(dev)
+        pos, grot, gx6 = torch.empty(frames, 24, 3, device=dev), torch.empty_like(rot), torch.empty_like(x6)
+        jf = frames * 24
+        t = {
+            "fk_fwd": (48.0, timed(lambda: check(lib.hmvae_fk_fwd(ptr(rot), 9, ptr(off), None, par, 24, frames, ptr(pos), None, stream())))),
+            "fk_bwd": (84.0, timed(lambda: check(lib.hmvae_fk_bwd(ptr(rot), 9, ptr(off), None, par, 24, frames, ptr(gp), None, ptr(grot), stream())))),
+            "rot6d_fwd": (60.0, timed(lambda: check(lib.hmvae_rot6d_fwd(ptr(x6), ptr(rot), jf, stream())))),
+            "rot6d_bwd": (84.0, timed(lambda: check(lib.hmvae_rot6d_bwd(ptr(x6), ptr(gr), ptr(gx6), jf, stream())))),
+        }
+        out["sizes"][str(frames)] = {k: {"us": round(sec * 1e6, 2), "gbs": round(bpj * jf / sec / 1e9, 1),
+                                         "frac": round(bpj * jf / sec / 1e9 / pk["hbm"], 4)} for k, (bpj, sec) in t.items()}
+        del x6, rot, gp, gr, pos, grot, gx6
+    big = out["sizes"][str(sizes[-1])]
+    out.update(frames=sizes[-1], fwd_gbs=big["fk_fwd"]["gbs"], bwd_gbs=big["fk_bwd"]["gbs"], fwd_frac=big["fk_fwd"]["frac"],
+               bwd_frac=big["fk_bwd"]["frac"], peak_gbs=pk["hbm"],
+               note="kernel time through the C ABI, CUDA events, %d back-to-back launches; algorithmic bytes 48 B/jf fwd, 84 B/jf bwd; "
+                    "the largest size moves 805 MB fwd / 1.4 GB bwd per launch (> 126 MB L2)" % iters)
+    return out
 
 
 def run_b200(args, hp):
@@ -290,7 +349,6 @@ def run_b200(args, hp):
         out = trainer.gen_update(data, hp, iters0)
     e1.record()
     barrier()
-    clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     loss_val = float(out[0])
 
@@ -308,6 +366,13 @@ def run_b200(args, hp):
     e1.record()
     barrier()
     ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    # the clock sampler (100 ms period) needs >= ~1 s under load: keep stepping (untimed) if the two timed regions were shorter
+    t_load = time.perf_counter()
+    while (ms + ms_e2e) * args.steps * 1e-3 + (time.perf_counter() - t_load) < 1.2:
+        for _ in range(20):
+            trainer.gen_update(data, hp, iters0)
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -315,42 +380,68 @@ def run_b200(args, hp):
     ms, ms_e2e = float(t[0]), float(t[1])
 
     # ---- per-kernel attribution (eager, CUDA events around each C-ABI call, after the timed region).  The steps contain the
-    #      gradient all-reduce, so EVERY rank runs them; only rank 0 reports.
+    #      gradient all-reduce, so EVERY rank runs them; only rank 0 reports.  Pass 1: one event pair per call (includes host
+    #      launch gaps) for the step breakdown.  Pass 2: weight-gradient overlap off and every conv entry point issued 8x back
+    #      to back inside its event pair -> device time per conv call, the roofline numerator's denominator.
     prof_steps = 5
-    with KernelTimer(_lib.lib) as kt:
-        saved, trainer._graphs = trainer._graphs, {}
-        sync_was = trainer._sync.enabled
-        trainer._sync.enabled = True
-        for _ in range(prof_steps):
-            trainer.gen_update(data, hp, iters0)
-        trainer._graphs = saved
-        trainer._sync.enabled = sync_was
-    barrier()
+
+    def eager_steps(kt_repeat):
+        with KernelTimer(_lib.lib, repeat=kt_repeat) as kt:
+            saved, trainer._graphs = trainer._graphs, {}
+            sync_was = trainer._sync.enabled
+            trainer._sync.enabled = True
+            for _ in range(prof_steps):
+                trainer.gen_update(data, hp, iters0)
+            trainer._graphs = saved
+            trainer._sync.enabled = sync_was
+        barrier()
+        return kt
+
+    kt = eager_steps(1)
+    ops._overlap["allowed"] = False
+    kt8 = eager_steps(8)
+    ops._overlap["allowed"] = True
     line = None
     if rank == 0:
-        summ = kt.summary()
-        conv = {k: summ.get(k, dict(ms=0.0, calls=0)) for k in KernelTimer.CONV}
+        summ, summ8 = kt.summary(), kt8.summary()
+        cls_ms = {c: sum(summ8.get(n, dict(ms=0.0))["ms"] for n in names) / prof_steps for c, names in KernelTimer.CONV.items()}
         fl_fwd = conv_flops_per_step(model, bs)
-        top = max(conv, key=lambda k: conv[k]["ms"])
-        top_ms = conv[top]["ms"] / prof_steps
+        top = max(cls_ms, key=lambda k: cls_ms[k])
+        top_ms = cls_ms[top]
         achieved = fl_fwd / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
         tf32_peak = pk["bf16"] / 2.0
         total_kernel_ms = sum(v["ms"] for v in summ.values()) / prof_steps
-        roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tf32_peak, "traffic": None,
-                    "peak_note": "TF32 dense taken as 1/2 of the %s bf16 figure (%.1f TF/s); conv math is %s" % (
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("conv_" + top, {}).get("dram_bytes_per_launch_set")
+        n_layers = len(model.enc.convs) + len(model.dec.convs)
+        roofline = {"kernel": "hmvae_conv_%s%s (all %d layers of one step = one launch set)" % (top, "" if args.conv_impl == "simt" else "_tc", n_layers),
+                    "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tf32_peak, "traffic": traffic,
+                    "peak_note": "TF32 dense taken as 1/2 of the %s bf16 burst figure (%.1f TF/s); conv math is %s.  At B=32 the layers "
+                                 "are latency / weight-bandwidth bound (7.2 GFLOP and 41 MB of weights per pass): see conv_large_batch for "
+                                 "the tensor-bound regime" % (
                         pk["src"], pk["bf16"], "fp32 CUDA-core" if args.conv_impl == "simt" else "auto (tcgen05 TF32 where supported, else fp32 CUDA-core)"),
                     "algorithmic_flops_per_launch_set": fl_fwd,
-                    "ms_per_step_in_kernel": top_ms,
+                    "ms_per_launch_set": top_ms,
+                    "conv_class_ms_per_step": {k: round(v, 4) for k, v in cls_ms.items()},
+                    "conv_class_tflops": {k: round(fl_fwd / (v * 1e-3) / 1e12, 2) if v > 0 else None for k, v in cls_ms.items()},
                     "kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])},
                     "kernel_ms_total_per_step_eager": total_kernel_ms,
-                    "conv_us_per_layer": kt.per_layer(prof_steps)}
+                    "conv_us_per_layer": kt8.per_layer(prof_steps)}
         fk = fk_sweep(dev, pk) if args.fk_sweep else None
+        big = None
+        if args.large_batch:
+            try:
+                big = inference_leg(model, hp, dev, pk)
+            except Exception as exc:        # reported, never fatal for the headline line
+                big = {"error": "%s: %s" % (type(exc).__name__, exc)}
         cpu = None
         if args.cpu_baseline:
-            sec, threads = cpu_reference_step_time(hp, bs, 10, 2)
+            sec, threads = cpu_reference_step_time(hp, bs, 60, 3)
             cpu = {"value": bs / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "10 timed steps of B=%d after 2 warm-up (oracle/hmvae_ref.py, torch CPU fp32, fwd+bwd+Adam)" % bs}
+                   "sample": "60 timed steps of B=%d after 3 warm-up (oracle/hmvae_ref.py, torch CPU fp32, fwd+bwd+Adam)" % bs}
         line = {"metric": METRIC, "value": world * bs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "tf32" if args.conv_impl != "simt" else "f32", "data": "synthetic",
@@ -362,7 +453,7 @@ def run_b200(args, hp):
                 "e2e": {"value": world * bs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(h6.numel() * 4 + hm.numel() * 4 + 8), "d2h_bytes_per_step": 20},
                 "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
-                "clocks": clocks, "roofline": roofline, "fk": fk, "cpu_baseline": cpu, "loss": loss_val}
+                "clocks": clocks, "roofline": roofline, "fk": fk, "conv_large_batch": big, "cpu_baseline": cpu, "loss": loss_val}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -383,6 +474,7 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-fk-sweep", dest="fk_sweep", action="store_false")
+    ap.add_argument("--no-large-batch", dest="large_batch", action="store_false")
     args = ap.parse_args()
     hp = load_cfg("len64_no_aug_hm_vae.yaml")
     if args.impl == "reference":
