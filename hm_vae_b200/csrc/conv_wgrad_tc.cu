@@ -7,14 +7,16 @@
 // rows are channels, the reduction index is the position p = t*Bt + b (time-major, sequence-minor, Bt % 4 == 0) and one
 // 16-byte element holds 4 consecutive sequences of the same time step, so
 //   * the 128 M-rows are 128 consecutive dy channels (several consecutive output joints),
+//   * the N columns are the channels of a WINDOW of consecutive input joints (N = wj * n_pad <= 128): a kind::tf32 M=128 K=8
+//     MMA from shared memory costs ~55-63 cycles for every N <= 128 (tools/umma_probe/rate.cu), so wide N is free,
 //   * tap k is a start-address shift of the x tile by k*Bt/4 K-chunks (stride-2 layers keep two input phases),
 //   * one tcgen05.mma consumes 8 positions; the accumulators of a whole tap group (L taps x N columns <= 512) stay in TMEM
 //     while the CTA streams over (batch group, time window) stages.
-// One CTA owns (M-slab, input joint n, tap group) => every dW element is written by exactly one thread (deterministic,
-// no atomics, masked blocks are never touched).  (M-slab, n) pairs without any neighbour relation are not launched.
+// One CTA owns (M-slab, input-joint window, tap group) => every dW element is written by exactly one thread (deterministic,
+// no atomics, masked blocks are never touched).  (M-slab, window) pairs without any neighbour relation are not launched.
 //
-//   conv_wgrad_prep_kernel : stages dy (with LeakyReLU') and the padded/upsampled/unpooled x as tf32 tiles, one contiguous
-//                            piece per (batch tile, CTA operand) so that the main kernel issues two bulk copies per stage.
+//   conv_wgrad_prep_kernel : stages dy (with LeakyReLU') and the padded/upsampled/unpooled x as tf32 tiles; x is staged once per
+//                            (stage, window, phase) for ALL taps, a tap group bulk-copies the contiguous chunk range it needs.
 //   conv_wgrad_tc_kernel   : warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (TMEM -> global dW).
 #include <string.h>
 
@@ -24,10 +26,11 @@ namespace hmvae {
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_STAGES = 4;
+constexpr int WG_MAX_WJ = 8;       // input joints per N window
 
 struct WgItem {      // one CTA
-  int slab, n, k0, L;
-  unsigned long long nbmask;    // bit j set <=> (j, n) is an unmasked block
+  int slab, win, k0, L;
+  unsigned long long nbmask[WG_MAX_WJ];    // [joint of the window]: bit j set <=> (j, n) is an unmasked block
 };
 
 struct WgArgs {
@@ -35,12 +38,14 @@ struct WgArgs {
   int B, T, T_out;
   int ckd;          // dy channels per joint padded to 8   (M side)
   int n_pad;        // x channels per joint padded to 16   (N side)
+  int wj, Nw, nwinN;  // input joints per N window, columns per window (= wj * n_pad <= 128), number of windows
   int dy_chunks;    // J * ckd / 4
   int slabs;        // ceil(dy_chunks / 32)
   int Bt, mtiles;   // sequences per stage (multiple of 4), number of batch groups
   int Tw, nwin;     // output time steps per stage, windows per sequence
   int Rd;           // dy positions per stage = Tw * Bt (multiple of 8)
-  int Rx;           // x positions per phase and stage (window of the tap group) = (Tw + win - 1) * Bt
+  int RxAll;        // staged x positions per phase and stage (all taps) = (Tw + span - 1) * Bt
+  int Rx;           // x positions per phase held in shared memory by one CTA (its tap group) = (Tw + win - 1) * Bt
   int nphase;       // 1 (stride 1) or 2
   int TG, Lmax;     // tap groups, taps per group
   int a_bytes, b_bytes, stage_bytes, stages;
@@ -78,15 +83,16 @@ __device__ __host__ __forceinline__ void wg_window(int s, int k0, int L, int pha
 
 // ---------------------------------------------------------------------------------------------- staging
 // stage st = mt * nwin + w  (batch group mt, time window w).  Position inside a stage: p = tl*Bt + b.
-// dyw[st][slab][Rd/4][128 rows][4]            rows = dy channels of the slab (padded numbering j*ckd + o)
-// xw [st][n][tg][phase][Rx/4][n_pad rows][4]  rows = channels of input joint n; tl counts from the window's first input index
+// dyw[st][slab][Rd/4][128 rows][4]           rows = dy channels of the slab (padded numbering j*ckd + o)
+// xw [st][win][phase][RxAll/4][Nw rows][4]   rows = (joint of the window, channel); positions count from the stage's first
+//                                            input index (stride 1: padded coordinate; stride 2: index inside the phase)
 __global__ void __launch_bounds__(256) conv_wgrad_prep_kernel(WgArgs p, const float* __restrict__ x,
                                                               const float* __restrict__ dy, const float* __restrict__ yact,
                                                               float4* __restrict__ dyw, float4* __restrict__ xw) {
   const ConvArgs& a = p.a;
   const int nst = p.mtiles * p.nwin;
   const long n_dy = (long)nst * p.slabs * (p.Rd / 4) * 128;
-  const long n_x = (long)nst * a.J * p.TG * p.nphase * (p.Rx / 4) * p.n_pad;
+  const long n_x = (long)nst * p.nwinN * p.nphase * (p.RxAll / 4) * p.Nw;
   const int Tq = p.T + 2 * a.p;
   const int bq = p.Bt / 4;
   for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < n_dy + n_x; it += (long)gridDim.x * blockDim.x) {
@@ -120,29 +126,25 @@ __global__ void __launch_bounds__(256) conv_wgrad_prep_kernel(WgArgs p, const fl
                              __uint_as_float(wg_tf32(v[3])));
     } else {
       long r = it - n_dy;
-      const int ulmax = p.Rx / p.Bt;
+      const int ulmax = p.RxAll / p.Bt;
       const int ul = (int)(r % ulmax); r /= ulmax;
       const int b4 = (int)(r % bq); r /= bq;
-      const int c = (int)(r % p.n_pad); r /= p.n_pad;
+      const int row = (int)(r % p.Nw); r /= p.Nw;
       const int phase = (int)(r % p.nphase); r /= p.nphase;
-      const int tg = (int)(r % p.TG); r /= p.TG;
-      const int n = (int)(r % a.J);
-      const int st = (int)(r / a.J);
+      const int win = (int)(r % p.nwinN);
+      const int st = (int)(r / p.nwinN);
       const int mt = st / p.nwin, w = st % p.nwin;
-      const int k0 = tg * p.Lmax;
-      const int L = (a.K - k0 < p.Lmax) ? a.K - k0 : p.Lmax;
-      int lo, cnt;
-      wg_window(a.s, k0, L, phase, &lo, &cnt);
-      const int u = w * p.Tw + lo + ul;                   // input index (stride 1: padded coordinate; stride 2: index in phase)
+      const int n = win * p.wj + row / p.n_pad, c = row % p.n_pad;
+      const int u = w * p.Tw + ul;            // stride 2: output step t reads index t + (k >> 1) of phase (k & 1)
       const int tp = (a.s == 1) ? u : 2 * u + phase;
-      if (cnt > 0 && ul < p.Tw + cnt - 1 && tp < Tq && c < a.ci) {
+      if (n < a.J && c < a.ci && tp < Tq) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const long bb = (long)mt * p.Bt + b4 * 4 + i;
           if (bb < p.B) v[i] = load_padded(x, a, bb, n, c, tp, p.T);
         }
       }
-      const long dst = (((((long)st * a.J + n) * p.TG + tg) * p.nphase + phase) * (p.Rx / 4) + (ul * bq + b4)) * p.n_pad + c;
+      const long dst = ((((long)st * p.nwinN + win) * p.nphase + phase) * (p.RxAll / 4) + (ul * bq + b4)) * p.Nw + row;
       xw[dst] = make_float4(__uint_as_float(wg_tf32(v[0])), __uint_as_float(wg_tf32(v[1])), __uint_as_float(wg_tf32(v[2])),
                             __uint_as_float(wg_tf32(v[3])));
     }
@@ -173,6 +175,18 @@ __global__ void __launch_bounds__(128) conv_bias_grad_kernel(ConvArgs a, const f
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
+__device__ __forceinline__ bool wg_elect() {      // one lane of a converged warp
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, const unsigned char* __restrict__ dyw,
                                                                       const unsigned char* __restrict__ xw,
                                                                       float* __restrict__ dw, int accumulate) {
@@ -183,7 +197,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
   const ConvArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const WgItem item = p.items[blockIdx.x];
-  const int nq = p.n_pad / 4;
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -202,52 +215,64 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
-  const int tg = item.k0 / p.Lmax;
   const int nst_all = p.mtiles * p.nwin;
   const int st_beg = blockIdx.y * p.plen;
   const int st_end = (st_beg + p.plen < nst_all) ? st_beg + p.plen : nst_all;
   if (p.psplits > 1) dw += (size_t)blockIdx.y * a.J * a.co * a.J * a.ci * a.K;      // this split's partial buffer
+  const uint32_t bq = (uint32_t)p.Bt / 4;
+  // the tap group's window of staged input positions, per phase: first shift `lo`, `cnt` distinct shifts
+  int lo[2] = {0, 0}, cnt[2] = {0, 0};
+  for (int ph = 0; ph < p.nphase; ++ph) wg_window(a.s, item.k0, item.L, ph, &lo[ph], &cnt[ph]);
+  const uint32_t ph_bytes_smem = (uint32_t)(p.Rx / 4) * p.Nw * 16;      // smem region of one phase
 
   if (warp == 0) {
     // =============================== producer ===============================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      uint32_t xbytes[2] = {0, 0};
+      for (int q = 0; q < p.nphase; ++q)
+        if (cnt[q] > 0) xbytes[q] = (uint32_t)(p.Tw + cnt[q] - 1) * bq * p.Nw * 16;
+      const size_t x_phase_stride = (size_t)(p.RxAll / 4) * p.Nw * 16;
       for (int mt = st_beg; mt < st_end; ++mt) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* st = smem_raw + (size_t)s * p.stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p.a_bytes + p.b_bytes));
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.a_bytes + xbytes[0] + xbytes[1]);
         bulk_g2s(st, dyw + ((size_t)mt * p.slabs + item.slab) * p.a_bytes, (uint32_t)p.a_bytes, &full_bar[s]);
-        bulk_g2s(st + p.a_bytes, xw + (((size_t)mt * a.J + item.n) * p.TG + tg) * p.b_bytes, (uint32_t)p.b_bytes, &full_bar[s]);
+        for (int q = 0; q < p.nphase; ++q)
+          if (xbytes[q])
+            bulk_g2s(st + p.a_bytes + (size_t)q * ph_bytes_smem,
+                     xw + (((size_t)mt * p.nwinN + item.win) * p.nphase + q) * x_phase_stride + (size_t)lo[q] * bq * p.Nw * 16,
+                     xbytes[q], &full_bar[s]);
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    // instruction descriptor: F32 accum, TF32 x TF32, both operands K-major, N = n_pad, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+    // instruction descriptor: F32 accum, TF32 x TF32, both operands K-major, N = Nw, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Nw >> 3) << 17) | ((128u >> 4) << 24);
+    const int ksteps = p.Rd / 8;
     int s = 0;
     uint32_t ph = 0;
     for (int mt = st_beg; mt < st_end; ++mt) {
       mbar_wait(&full_bar[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_base = smem_u32(smem_raw + (size_t)s * p.stage_bytes);
+      const uint32_t b_base = a_base + p.a_bytes;
+      // K-major, no swizzle: LBO = stride between 16-byte K chunks (= rows*16), SBO = stride between 8-row groups (128 B)
+      const uint64_t adesc0 = wg_desc(a_base, 128 * 16, 128);
+      const uint64_t bdesc0 = wg_desc(b_base, (uint32_t)p.Nw * 16, 128);
+      const uint32_t acc0 = (mt > st_beg) ? 1u : 0u;
       if (lane == 0) {
-        const uint32_t a_base = smem_u32(smem_raw + (size_t)s * p.stage_bytes);
-        const uint32_t b_base = a_base + p.a_bytes;
-        // K-major, no swizzle: LBO = stride between 16-byte K chunks (= rows*16), SBO = stride between 8-row groups (128 B)
-        const uint64_t adesc0 = wg_desc(a_base, 128 * 16, 128);
-        const uint64_t bdesc0 = wg_desc(b_base, (uint32_t)p.n_pad * 16, 128);
-        const int ksteps = p.Rd / 8;
-        const uint32_t bq = (uint32_t)p.Bt / 4;
+        // single-thread issue loop (a converged-warp elect.sync variant was measured slower inside the real kernels)
         for (int t = 0; t < item.L; ++t) {
           const int k = item.k0 + t;
-          int lo, cnt, phase = 0, shift;
-          if (a.s == 1) { shift = t; }
-          else { phase = k & 1; wg_window(2, item.k0, item.L, phase, &lo, &cnt); shift = (k >> 1) - lo; }
+          const int phase = (a.s == 1) ? 0 : (k & 1);
+          const int shift = ((a.s == 1) ? k : (k >> 1)) - lo[phase];
           uint64_t ad = adesc0;
-          uint64_t bd = bdesc0 + (uint32_t)(phase * (p.Rx / 4) + shift * bq) * (uint32_t)p.n_pad;
-          const uint32_t d_addr = tmem_base + (uint32_t)(t * p.n_pad);
-          uint32_t acc = (mt > st_beg) ? 1u : 0u;
+          uint64_t bd = bdesc0 + (uint32_t)(phase * (p.Rx / 4) + shift * (int)bq) * (uint32_t)p.Nw;
+          const uint32_t d_addr = tmem_base + (uint32_t)(t * p.Nw);
+          uint32_t acc = acc0;
 #pragma unroll 4
           for (int ks = 0; ks < ksteps; ++ks) {
             asm volatile(
@@ -260,7 +285,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
                 : "memory");
             acc = 1;
             ad += 2 * 128;                     // 8 positions = 2 K-chunks of 128 rows x 16 B (16-byte units)
-            bd += 2 * (uint32_t)p.n_pad;
+            bd += 2 * (uint32_t)p.Nw;
           }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s]))
@@ -274,19 +299,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
     __syncwarp();
   } else {
     // =============================== epilogue (warps 2..5): TMEM -> dW ===============================
+    // (A shared-memory transpose that makes every warp write one dW row at a time was measured SLOWER than these direct
+    //  per-thread stores -- 0.77 vs 0.55 ms per step -- the row loop serialises; kept simple.)
     mbar_wait(&accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int lq = warp & 3;
     const int m = lq * 32 + lane;
     const int gch = item.slab * 128 + m;                 // dy channel (padded numbering)
     const int j = gch / p.ckd, o = gch % p.ckd;
-    const bool valid = j < a.J && o < a.co && ((item.nbmask >> j) & 1ull);
+    const bool rowok = j < a.J && o < a.co;
     const int Cin = a.J * a.ci;
-    float* wrow = dw + ((long)(valid ? j * a.co + o : 0) * Cin + item.n * a.ci) * a.K + item.k0;
-    for (int c16 = 0; c16 < p.n_pad; c16 += 16) {
+    float* wrow0 = dw + ((long)(rowok ? j * a.co + o : 0) * Cin) * a.K + item.k0;
+    for (int c16 = 0; c16 < p.Nw; c16 += 16) {
+      const int wjl = c16 / p.n_pad;                     // n_pad is a multiple of 16: a 16-column group lies inside one joint
+      const int n = item.win * p.wj + wjl;
+      const int cbase = c16 - wjl * p.n_pad;
+      if (n >= a.J || cbase >= a.ci) continue;           // warp-uniform: padding columns
+      const bool valid = rowok && ((item.nbmask[wjl] >> j) & 1ull);      // warp-divergent only in the stores
       for (int t = 0; t < item.L; ++t) {
         uint32_t r[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * p.n_pad + c16);
+        const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * p.Nw + c16);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -294,9 +326,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (valid) {
+          float* wrow = wrow0 + (long)n * a.ci * a.K;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int c = c16 + i;
+            const int c = cbase + i;
             if (c < a.ci) {
               float* dst = wrow + (long)c * a.K + t;
               const float v = __uint_as_float(r[i]);
@@ -350,58 +383,87 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
   p.ckd = rup(a.co, 8);
   p.n_pad = rup(a.ci, 16);
   if (p.n_pad > 256) return false;
+  // N window: as many consecutive input joints as fit 128 columns (an MMA costs the same for every N <= 128)
+  p.wj = 128 / p.n_pad;
+  if (p.wj < 1) p.wj = 1;
+  if (p.wj > WG_MAX_WJ) p.wj = WG_MAX_WJ;
+  if (p.wj > a.J) p.wj = a.J;
+  p.Nw = p.wj * p.n_pad;
+  p.nwinN = (a.J + p.wj - 1) / p.wj;
   p.dy_chunks = a.J * p.ckd / 4;
   p.slabs = (p.dy_chunks + 31) / 32;
   p.nphase = a.s;
-  // taps per group: L * n_pad accumulator columns <= 512
-  p.Lmax = 512 / p.n_pad;
+  // taps per group: L * Nw accumulator columns <= 512
+  p.Lmax = 512 / p.Nw;
+  if (p.Lmax > 16) p.Lmax = 16;                     // epilogue transpose tile: 128 x (16 * L + 1) floats <= 132 KB
   if (p.Lmax > a.K) p.Lmax = a.K;
   p.TG = (a.K + p.Lmax - 1) / p.Lmax;
   p.Lmax = (a.K + p.TG - 1) / p.TG;                 // balance the groups
-  int cols = p.Lmax * p.n_pad, pow2 = 32;
+  int cols = p.Lmax * p.Nw, pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   if (pow2 > 512) return false;
   p.tmem_cols = pow2;
   // a stage = Bt sequences (multiple of 4) x Tw output time steps, ~64 positions
   p.Tw = p.T_out < 16 ? p.T_out : 16;
   p.nwin = (p.T_out + p.Tw - 1) / p.Tw;
-  p.Bt = rup(64 / p.Tw > 4 ? 64 / p.Tw : 4, 4);
-  if (p.Bt > rup(B, 4)) p.Bt = rup(B, 4);
-  while ((p.Tw * p.Bt) % 8 != 0) p.Bt += 4;           // K steps of 8 positions (extra sequences are zero columns)
+  const int span = (a.s == 1) ? a.K : ((a.K - 1) >> 1) + 1;          // distinct input shifts over all taps (per phase)
+  int win = 1;                                                        // largest shift window of one (tap group, phase)
+  for (int tg = 0; tg < p.TG; ++tg) {
+    const int k0 = tg * p.Lmax;
+    const int L = (a.K - k0 < p.Lmax) ? a.K - k0 : p.Lmax;
+    for (int ph = 0; ph < p.nphase; ++ph) {
+      int lo, cnt;
+      wg_window(a.s, k0, L, ph, &lo, &cnt);
+      if (cnt > win) win = cnt;
+    }
+  }
+  // sequences per stage: start at ~64 positions, shrink (multiples of 4, Tw*Bt % 8 == 0) until >= 3 stages fit
+  auto size_stage = [&](int bt) {
+    p.Bt = bt;
+    p.Rd = p.Tw * p.Bt;
+    p.RxAll = (p.Tw + span - 1) * p.Bt;
+    p.Rx = (p.Tw + win - 1) * p.Bt;
+    p.a_bytes = (p.Rd / 4) * 128 * 16;
+    p.b_bytes = p.nphase * (p.Rx / 4) * p.Nw * 16;
+    p.stage_bytes = rup(p.a_bytes + p.b_bytes, 128);
+    p.stages = (200 * 1024) / p.stage_bytes;
+  };
+  int bt0 = rup(64 / p.Tw > 4 ? 64 / p.Tw : 4, 4);
+  if (bt0 > rup(B, 4)) bt0 = rup(B, 4);
+  while ((p.Tw * bt0) % 8 != 0) bt0 += 4;
+  size_stage(bt0);
+  for (int bt = bt0 - 4; p.stages < 3 && bt >= 4; bt -= 4)
+    if ((p.Tw * bt) % 8 == 0) size_stage(bt);
   p.mtiles = (B + p.Bt - 1) / p.Bt;
-  p.Rd = p.Tw * p.Bt;
-  const int win = (a.s == 1) ? p.Lmax : (p.Lmax + 1) / 2 + 1;
-  p.Rx = (p.Tw + win - 1) * p.Bt;
-  p.a_bytes = (p.Rd / 4) * 128 * 16;
-  p.b_bytes = p.nphase * (p.Rx / 4) * p.n_pad * 16;
-  p.stage_bytes = rup(p.a_bytes + p.b_bytes, 128);
-  p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   if (p.stages < 2) return false;
   if (p.Rd * 16 >= (1 << 18) || p.Rx * 16 >= (1 << 18)) return false;
   // work items
-  const int jps = 128 / p.ckd;                       // joints per slab (ckd divides 128 only for 8,16,32,64; handle generally below)
-  (void)jps;
   std::vector<WgItem> items;
   for (int slab = 0; slab < p.slabs; ++slab) {
     const int ch0 = slab * 128, ch1 = ch0 + 128;
-    for (int n = 0; n < a.J; ++n) {
-      unsigned long long mask = 0;
+    for (int win_i = 0; win_i < p.nwinN; ++win_i) {
+      WgItem it;
+      memset(&it, 0, sizeof(it));
       bool any = false;
-      for (int j = 0; j < a.J; ++j) {
-        bool nb = false;
-        for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m) nb |= plan->nb_idx[m] == n;
-        if (!nb) continue;
-        mask |= 1ull << j;
-        const int c0 = j * p.ckd, c1 = c0 + a.co;    // channel range of joint j in the padded numbering
-        if (c0 < ch1 && c1 > ch0) any = true;
+      for (int wl = 0; wl < p.wj; ++wl) {
+        const int n = win_i * p.wj + wl;
+        if (n >= a.J) break;
+        unsigned long long mask = 0;
+        for (int j = 0; j < a.J; ++j) {
+          bool nb = false;
+          for (int m = plan->nb_off[j]; m < plan->nb_off[j + 1]; ++m) nb |= plan->nb_idx[m] == n;
+          if (!nb) continue;
+          mask |= 1ull << j;
+          const int c0 = j * p.ckd, c1 = c0 + a.co;    // channel range of joint j in the padded numbering
+          if (c0 < ch1 && c1 > ch0) any = true;
+        }
+        it.nbmask[wl] = mask;
       }
       if (!any) continue;
       for (int tg = 0; tg < p.TG; ++tg) {
-        WgItem it;
-        it.slab = slab; it.n = n; it.k0 = tg * p.Lmax;
+        it.slab = slab; it.win = win_i; it.k0 = tg * p.Lmax;
         it.L = (a.K - it.k0 < p.Lmax) ? a.K - it.k0 : p.Lmax;
-        it.nbmask = mask;
         if (it.L > 0) items.push_back(it);
       }
     }
@@ -413,6 +475,8 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
     int splits = p.nitems > 0 ? num_sms() / p.nitems : 1;
     if (splits > nst / 4) splits = nst / 4;
     if (splits > 8) splits = 8;
+    const long dense_bytes = (long)a.J * a.co * a.J * a.ci * a.K * 4;
+    if (dense_bytes * splits > (24L << 20)) splits = (int)((24L << 20) / dense_bytes);   // partial buffers + reduce cost too much
     if (splits < 1) splits = 1;
     p.plen = (nst + splits - 1) / splits;
     p.psplits = (nst + p.plen - 1) / p.plen;
@@ -455,7 +519,7 @@ static bool wg_geometry(const hmvae_conv_plan* plan, int B, int T, WgArgs* out) 
 }
 
 static long wg_dy_bytes(const WgArgs& p) { return (long)p.mtiles * p.nwin * p.slabs * p.a_bytes; }
-static long wg_x_bytes(const WgArgs& p) { return (long)p.mtiles * p.nwin * p.a.J * p.TG * p.b_bytes; }
+static long wg_x_bytes(const WgArgs& p) { return (long)p.mtiles * p.nwin * p.nwinN * p.nphase * (p.RxAll / 4) * p.Nw * 16; }
 static long wg_part_bytes(const WgArgs& p) {
   return p.psplits > 1 ? (long)p.psplits * p.a.J * p.a.co * p.a.J * p.a.ci * p.a.K * 4 : 0;
 }
@@ -494,7 +558,10 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
     int rc = check_launch("conv_bias_grad");
     if (rc) return rc;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  size_t smem = (size_t)p.stages * p.stage_bytes;
+  const size_t epi = (size_t)128 * (16 * p.Lmax + 1) * 4;       // the epilogue's transpose tile reuses the stage buffers
+  if (epi > smem) smem = epi;
+  smem += 1024;
   HMVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* part = reinterpret_cast<float*>(xw + wg_x_bytes(p));
   dim3 grid(p.nitems, p.psplits);
