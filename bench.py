@@ -448,7 +448,7 @@ def run_b200(args, hp):
                 "config": {"workload": "configs/len64_no_aug_hm_vae.yaml train step (fwd+bwd+allreduce+Adam), B=%d per GPU, "
                                        "T=64, 24-joint SMPL, random-init weights" % bs,
                            "global_batch": world * bs, "parallelism": "dp%d" % world, "cuda_graph": bool(args.graph),
-                           "conv_impl": args.conv_impl,
+                           "conv_impl": args.conv_impl, "data_parallel": trainer.dp_mode,
                            "l2": "no flush: per-step working set (params+grads+Adam state ~265 MB) exceeds the 126 MB L2"},
                 "e2e": {"value": world * bs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(h6.numel() * 4 + hm.numel() * 4 + 8), "d2h_bytes_per_step": 20},

@@ -55,6 +55,14 @@ class AdamTensor(Structure):
     _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("numel", c_long)]
 
 
+DP_MAX_WORLD, DP_MAX_RANGES = 8, 64
+
+
+class DpPeers(Structure):
+    _fields_ = [("world", c_int), ("rank", c_int), ("grad", c_void_p * DP_MAX_WORLD), ("param", c_void_p * DP_MAX_WORLD),
+                ("flags", c_void_p * DP_MAX_WORLD)]
+
+
 P = c_void_p
 IP = POINTER(c_int)
 _SIGS = {
@@ -101,6 +109,12 @@ _SIGS = {
     "hmvae_traj_fwdbwd": (c_int, [P, P, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, c_float, c_float, P, P, P]),
     "hmvae_adam_step": (c_int, [POINTER(AdamTensor), c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
     "hmvae_adam_step_dyn": (c_int, [POINTER(AdamTensor), c_int, P, c_float, c_float, c_float, c_float, c_float, P]),
+    "hmvae_dp_adam_step": (c_int, [POINTER(DpPeers), P, P, POINTER(c_long), c_int, P, c_float, c_float, c_float, c_float, c_float, P, P]),
+    "hmvae_ipc_alloc": (c_int, [c_long, POINTER(c_void_p)]),
+    "hmvae_ipc_free": (c_int, [c_void_p]),
+    "hmvae_ipc_get_handle": (c_int, [c_void_p, P]),
+    "hmvae_ipc_open_handle": (c_int, [P, POINTER(c_void_p)]),
+    "hmvae_ipc_close_handle": (c_int, [c_void_p]),
 }
 EXPORTS = sorted(_SIGS)
 

@@ -1,0 +1,195 @@
+// Data-parallel optimiser step fused with its collective, over NVLink peer memory.   sm_100a.
+//
+// Replaces  [NCCL all-reduce of 52.9 MB of gradients] -> [Adam over 52.9 MB x (p, g, m, v)]  (DataParallel's gather +
+// torch.optim.Adam in the reference, train_motion_vae.py:49-53 / trainer_motion_vae.py:29-31, 92-93) by ONE kernel per rank:
+//
+//   rank r owns the r-th share of the (live) parameter elements.  For each owned element it
+//     1. reads the gradient from EVERY rank's gradient arena (peer loads through NVLink; fixed order 0..W-1 => every element
+//        is reduced exactly once, by one rank, deterministically)                               -- the reduce-scatter,
+//     2. applies torch.optim.Adam (L2 decay added to the gradient) with its LOCAL slice of m and v (optimiser state and
+//        optimiser arithmetic are sharded W ways)                                                -- the optimiser,
+//     3. stores the new parameter value into EVERY rank's parameter arena (peer stores)          -- the all-gather.
+//
+//   Cross-rank ordering uses two flag barriers in peer memory (monotonic epoch numbers, release/acquire at system scope):
+//     entry: "my gradients are final"  -- rank q's stream order guarantees that when its kernel starts;
+//     exit : "I have finished reading your gradients and writing your parameters" -- the LAST CTA of each rank signals and
+//            waits, so a rank's kernel (hence its next forward pass / its next backward pass overwriting the gradient arena)
+//            cannot complete before all its peers are done with its memory.
+//   No NCCL call, no host synchronisation: the kernel is CUDA-graph capturable (the epoch lives in device memory).
+//   A waiter that sees no signal for HMVAE_DP_TIMEOUT_NS raises state[2] and carries on (results are then wrong, but the GPU
+//   never hangs); the host checks the flag.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace hmvae {
+
+constexpr unsigned long long DP_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct DpArgs {
+  int world, rank;
+  const float* grad[HMVAE_DP_MAX_WORLD];
+  float* param[HMVAE_DP_MAX_WORLD];
+  unsigned int* flags[HMVAE_DP_MAX_WORLD];      // [2 * world] per rank: entry flags, exit flags (indexed by the SIGNALLING rank)
+  long beg[HMVAE_DP_MAX_RANGES], end[HMVAE_DP_MAX_RANGES];   // owned element ranges (multiples of 4, 16-byte aligned)
+  int nranges;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// waits until *flag >= epoch (wrap-safe signed difference); false on timeout
+__device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int epoch) {
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned int spins = 0;
+  while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > DP_TIMEOUT_NS) return false;
+    __nanosleep(64);
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restrict__ m, float* __restrict__ v,
+                                                      const float* __restrict__ dyn2, float beta1, float beta2, float eps,
+                                                      float wd, float gscale, unsigned int* __restrict__ state) {
+  // state[0] = epoch of the last completed call, state[1] = CTAs done in this call, state[2] = timeout flag
+  __shared__ unsigned int s_epoch;
+  const int W = A.world, R = A.rank;
+  if (threadIdx.x == 0) {
+    const unsigned int epoch = state[0] + 1u;
+    if (W > 1) {
+      if (blockIdx.x == 0)
+        for (int q = 0; q < W; ++q) st_release_sys(A.flags[q] + R, epoch);                  // my gradients are final
+      for (int q = 0; q < W; ++q)
+        if (!wait_flag(A.flags[R] + q, epoch)) atomicExch(state + 2, 1u);
+    }
+    s_epoch = epoch;
+  }
+  __syncthreads();
+  const float lr_over_bc1 = dyn2[0], inv_sqrt_bc2 = dyn2[1];
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nthreads = (long)gridDim.x * blockDim.x;
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    gg = gg * gscale + wd * pp;
+    mm = mm + (gg - mm) * (1.f - beta1);
+    vv = vv * beta2 + (1.f - beta2) * gg * gg;
+    const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+    pp = pp - lr_over_bc1 * (mm / denom);
+  };
+  for (int r = 0; r < A.nranges; ++r) {
+    const long b4 = A.beg[r] >> 2, e4 = A.end[r] >> 2;
+    for (long i = b4 + tid; i < e4; i += nthreads) {
+      float4 G = __ldcg(reinterpret_cast<const float4*>(A.grad[0]) + i);
+      for (int q = 1; q < W; ++q) {
+        const float4 g2 = __ldcg(reinterpret_cast<const float4*>(A.grad[q]) + i);
+        G.x += g2.x; G.y += g2.y; G.z += g2.z; G.w += g2.w;
+      }
+      float4 P = reinterpret_cast<const float4*>(A.param[R])[i];
+      float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+      upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+      reinterpret_cast<float4*>(m)[i] = M;
+      reinterpret_cast<float4*>(v)[i] = V;
+      for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(A.param[q])[i] = P;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int done = atomicAdd(state + 1, 1u);
+    if (done == gridDim.x - 1) {                       // last CTA of this rank
+      __threadfence_system();
+      const unsigned int epoch = s_epoch;
+      if (W > 1) {
+        for (int q = 0; q < W; ++q) st_release_sys(A.flags[q] + W + R, epoch);               // done with your memory
+        for (int q = 0; q < W; ++q)
+          if (!wait_flag(A.flags[R] + W + q, epoch)) atomicExch(state + 2, 1u);
+      }
+      state[1] = 0;
+      state[0] = epoch;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace hmvae
+
+using namespace hmvae;
+
+extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges,
+                                  const float* dyn2, float beta1, float beta2, float eps, float weight_decay,
+                                  float grad_scale, unsigned int* state, void* stream) {
+  if (!peers || !m || !v || !dyn2 || !state || (nranges > 0 && !ranges)) return fail_arg("dp_adam_step: null pointer");
+  if (peers->world < 1 || peers->world > HMVAE_DP_MAX_WORLD || peers->rank < 0 || peers->rank >= peers->world)
+    return fail_arg("dp_adam_step: bad world / rank");
+  if (nranges < 0 || nranges > HMVAE_DP_MAX_RANGES) return fail_arg("dp_adam_step: too many ranges");
+  DpArgs A;
+  A.world = peers->world;
+  A.rank = peers->rank;
+  for (int q = 0; q < HMVAE_DP_MAX_WORLD; ++q) {
+    const bool on = q < peers->world;
+    A.grad[q] = on ? peers->grad[q] : nullptr;
+    A.param[q] = on ? peers->param[q] : nullptr;
+    A.flags[q] = on ? peers->flags[q] : nullptr;
+    if (on && (!A.grad[q] || !A.param[q] || (peers->world > 1 && !A.flags[q]))) return fail_arg("dp_adam_step: null peer pointer");
+    if (on && (!aligned16(A.grad[q]) || !aligned16(A.param[q]))) return fail_arg("dp_adam_step: arenas must be 16-byte aligned");
+  }
+  if (!aligned16(m) || !aligned16(v)) return fail_arg("dp_adam_step: m / v must be 16-byte aligned");
+  long total = 0;
+  A.nranges = nranges;
+  for (int r = 0; r < nranges; ++r) {
+    A.beg[r] = ranges[2 * r];
+    A.end[r] = ranges[2 * r + 1];
+    if (A.beg[r] < 0 || A.end[r] < A.beg[r] || (A.beg[r] & 3) || (A.end[r] & 3)) return fail_arg("dp_adam_step: ranges must be multiples of 4");
+    total += A.end[r] - A.beg[r];
+  }
+  // every rank must launch (the flag barriers pair up) even if it owns nothing; all CTAs are resident (<= 4 per SM)
+  long blocks = (total / 4 + 255) / 256;
+  const long cap = (long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  dp_adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, m, v, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state);
+  return check_launch("dp_adam_step");
+}
+
+// ---------------------------------------------------------------- peer memory plumbing (CUDA IPC), used when
+// torch.distributed._symmetric_memory is not usable in the container
+extern "C" int hmvae_ipc_alloc(long bytes, void** ptr) {
+  if (!ptr || bytes <= 0) return fail_arg("ipc_alloc: bad arguments");
+  HMVAE_CUDA(cudaMalloc(ptr, (size_t)bytes));
+  HMVAE_CUDA(cudaMemset(*ptr, 0, (size_t)bytes));
+  HMVAE_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+extern "C" int hmvae_ipc_free(void* ptr) {
+  if (ptr) HMVAE_CUDA(cudaFree(ptr));
+  return 0;
+}
+extern "C" int hmvae_ipc_get_handle(void* ptr, unsigned char* handle64) {
+  if (!ptr || !handle64) return fail_arg("ipc_get_handle: null pointer");
+  cudaIpcMemHandle_t h;
+  HMVAE_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+extern "C" int hmvae_ipc_open_handle(const unsigned char* handle64, void** ptr) {
+  if (!handle64 || !ptr) return fail_arg("ipc_open_handle: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  HMVAE_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+extern "C" int hmvae_ipc_close_handle(void* ptr) {
+  if (ptr) HMVAE_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}

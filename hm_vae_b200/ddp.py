@@ -58,6 +58,7 @@ def make_buckets(named_params, n_buckets=4):
 
 class BucketedAllReduce:
     """Overlapped gradient all-reduce.  Usage per step:  sync.begin(); <backward>; sync.finish()."""
+    fused = False
 
     def __init__(self, module, n_buckets=4, live=None, group=None):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1

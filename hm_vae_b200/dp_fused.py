@@ -1,0 +1,281 @@
+"""Data-parallel Adam fused with its collective over NVLink peer memory (``hmvae_dp_adam_step``, csrc/dp.cu).
+
+Replaces ``torch.nn.DataParallel`` + ``torch.optim.Adam`` of the reference (train_motion_vae.py:49-53,
+trainer_motion_vae.py:29-31, 92-93).  Parameters and gradients of all trainable tensors live in two flat, symmetric
+arenas per rank (same offset = same element on every rank), mapped into every peer's address space
+(``torch.distributed._symmetric_memory``, or CUDA IPC through the C ABI when that is unavailable).  The weight / bias
+gradient kernels write straight into the gradient arena (``ops.grad_buffer``), so one kernel per step does
+reduce-scatter -> sharded Adam -> all-gather; there is no NCCL call on the step path and the whole step, collective
+included, is one CUDA graph.
+
+The pure-Python helpers (``arena_layout``, ``merge_ranges``, ``owned_ranges``) are covered by the CPU tests (gloo, world 2).
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+ALIGN = 4          # elements: every tensor starts on a 16-byte boundary; ranges are multiples of 4 (float4 path)
+
+
+def arena_layout(numels):
+    """[numel] -> ([offset], total) with every offset (and the total) a multiple of ALIGN."""
+    offs, cur = [], 0
+    for n in numels:
+        offs.append(cur)
+        cur += (int(n) + ALIGN - 1) // ALIGN * ALIGN
+    return offs, cur
+
+
+def merge_ranges(ranges):
+    """Sorted, disjoint, adjacent-merged [begin, end) list."""
+    out = []
+    for b, e in sorted(ranges):
+        if e <= b:
+            continue
+        if out and b <= out[-1][1]:
+            out[-1][1] = max(out[-1][1], e)
+        else:
+            out.append([b, e])
+    return [tuple(r) for r in out]
+
+
+def rank_share(total, rank, world):
+    """Static ownership: rank r owns arena elements [lo, hi) -- independent of which parameters are live in a given step, so
+    a rank's slice of the Adam moments never migrates."""
+    units = total // ALIGN
+    return (units * rank) // world * ALIGN, (units * (rank + 1)) // world * ALIGN
+
+
+def owned_ranges(live, rank, world, total):
+    """Live element ranges intersected with the rank's static share.  Over all ranks: disjoint, union == live."""
+    lo, hi = rank_share(total, rank, world)
+    out = []
+    for b, e in merge_ranges(live):
+        s, t = max(b, lo), min(e, hi)
+        if t > s:
+            out.append((s, t))
+    return out
+
+
+class _RawCudaBuffer:
+    """A device allocation owned by the C library, exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, numel, typestr):
+        self.ptr, self.numel = ptr, numel
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerArenas:
+    """grad / param arenas (float32[numel]) and a flag pad (uint32) mapped on every rank of ``group``."""
+
+    def __init__(self, numel, device, group=None, prefer="symm"):
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.numel, self.device, self.group = numel, device, group
+        self.backend = None
+        self._keep = []
+        if self.world == 1:
+            self.grad = torch.zeros(numel, device=device, dtype=torch.float32)
+            self.param = torch.zeros(numel, device=device, dtype=torch.float32)
+            self.flags = torch.zeros(64, device=device, dtype=torch.int32)
+            self.grad_ptrs, self.param_ptrs, self.flag_ptrs = [self.grad.data_ptr()], [self.param.data_ptr()], [self.flags.data_ptr()]
+            self.backend = "local"
+            return
+        err = None
+        if prefer == "symm":
+            try:
+                self._init_symm()
+                return
+            except Exception as exc:         # noqa: BLE001 -- fall through to CUDA IPC
+                err = exc
+        try:
+            self._init_ipc()
+        except Exception as exc2:            # noqa: BLE001
+            raise _lib.HmvaeError("peer memory unavailable: symmetric memory: %r; CUDA IPC: %r" % (err, exc2))
+
+    def _init_symm(self):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = self.group if self.group is not None else dist.group.WORLD
+        bufs, hdls = [], []
+        for n, dt in ((self.numel, torch.float32), (self.numel, torch.float32), (64, torch.int32)):
+            t = symm_mem.empty(n, dtype=dt, device=self.device)
+            t.zero_()
+            hdls.append(symm_mem.rendezvous(t, group))
+            bufs.append(t)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.grad, self.param, self.flags = bufs
+        self.grad_ptrs, self.param_ptrs, self.flag_ptrs = [list(h.buffer_ptrs) for h in hdls]
+        self._keep = hdls
+        self.backend = "symmetric_memory"
+
+    def _init_ipc(self):
+        lib = _lib.lib
+        ptrs = []
+        for nbytes in (self.numel * 4, self.numel * 4, 64 * 4):
+            p = ctypes.c_void_p()
+            _lib.check(lib.hmvae_ipc_alloc(nbytes, ctypes.byref(p)), "ipc_alloc")
+            ptrs.append(p.value)
+        handles = []
+        for p in ptrs:
+            h = (ctypes.c_ubyte * 64)()
+            _lib.check(lib.hmvae_ipc_get_handle(ctypes.c_void_p(p), h), "ipc_get_handle")
+            handles.append(bytes(h))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles, group=self.group)
+        tables = [[], [], []]
+        for q in range(self.world):
+            for k in range(3):
+                if q == self.rank:
+                    tables[k].append(ptrs[k])
+                else:
+                    out = ctypes.c_void_p()
+                    hb = (ctypes.c_ubyte * 64).from_buffer_copy(gathered[q][k])
+                    _lib.check(lib.hmvae_ipc_open_handle(hb, ctypes.byref(out)), "ipc_open_handle")
+                    tables[k].append(out.value)
+        self.grad_ptrs, self.param_ptrs, self.flag_ptrs = tables
+        self._raw = [_RawCudaBuffer(ptrs[0], self.numel, "<f4"), _RawCudaBuffer(ptrs[1], self.numel, "<f4"), _RawCudaBuffer(ptrs[2], 64, "<i4")]
+        self.grad = torch.as_tensor(self._raw[0], device=self.device)
+        self.param = torch.as_tensor(self._raw[1], device=self.device)
+        self.flags = torch.as_tensor(self._raw[2], device=self.device)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.backend = "cuda_ipc"
+
+
+class FusedDataParallelAdam:
+    """torch.optim.Adam(lr, betas, eps, weight_decay) over flat peer-mapped arenas; ``step_dyn`` is the fused
+    reduce-scatter + Adam + all-gather kernel.  Same host interface as ``ops.FusedAdam`` (advance / step_dyn / zero_grad)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None, prefer="symm"):
+        from . import ops
+
+        self.params = [p for p in params]
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.step_count = 0
+        self.param_groups = [dict(lr=lr)]
+        dev = self.params[0].device
+        self.offsets, self.numel = arena_layout([p.numel() for p in self.params])
+        self.arenas = PeerArenas(self.numel, dev, group=group, prefer=prefer)
+        self.world, self.rank = self.arenas.world, self.arenas.rank
+        self.m = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        self.state = torch.zeros(4, device=dev, dtype=torch.int32)
+        self._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._dyn_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        # parameters move into the arena (identical values on every rank are the caller's job: broadcast first)
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                view = self.arenas.param[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = None
+        # ... and the gradient kernels write into the gradient arena
+        for p, off in zip(self.params, self.offsets):
+            ops.register_grad_buffer(p, self.arenas.grad, off)
+        peers = _lib.DpPeers()
+        peers.world, peers.rank = self.world, self.rank
+        for q in range(self.world):
+            peers.grad[q] = self.arenas.grad_ptrs[q]
+            peers.param[q] = self.arenas.param_ptrs[q]
+            peers.flags[q] = self.arenas.flag_ptrs[q]
+        self._peers = peers
+        self._range_cache = {}
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def close(self):
+        from . import ops
+
+        ops.unregister_grad_buffers(self.arenas.grad)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001 -- interpreter shutdown
+            pass
+
+    # ---- same surface as ops.FusedAdam
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+
+    def advance(self, lr=None):
+        self.step_count += 1
+        lr = self.param_groups[0]["lr"] if lr is None else lr
+        self._dyn_host[0] = lr / (1.0 - self.betas[0] ** self.step_count)
+        self._dyn_host[1] = 1.0 / (1.0 - self.betas[1] ** self.step_count) ** 0.5
+
+    def _live_ranges(self):
+        """Live = parameters that received a gradient this step.  Gradients that autograd did not place in the arena (it
+        clones a gradient it cannot steal) are copied in."""
+        key, live = [], []
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            if p.grad is None:
+                continue
+            n = p.numel()
+            if p.grad.data_ptr() != self.arenas.grad.data_ptr() + 4 * off:
+                self.arenas.grad[off:off + n].view(p.shape).copy_(p.grad)
+            key.append(i)
+            live.append((off, off + (n + ALIGN - 1) // ALIGN * ALIGN))
+        key = tuple(key)
+        if key not in self._range_cache:
+            own = owned_ranges(live, self.rank, self.world, self.numel)
+            if len(own) > _lib.DP_MAX_RANGES:
+                raise _lib.HmvaeError("too many gradient ranges (%d) for hmvae_dp_adam_step" % len(own))
+            flat = (ctypes.c_long * (2 * max(len(own), 1)))()
+            for k, (b, e) in enumerate(own):
+                flat[2 * k], flat[2 * k + 1] = b, e
+            self._range_cache[key] = (flat, len(own))
+        return self._range_cache[key]
+
+    def step_dyn(self, grad_scale=None):
+        """Device side (capturable).  ``grad_scale`` defaults to 1/world (mean of the per-rank gradients)."""
+        from . import ops
+
+        flat, n = self._live_ranges()
+        self._dyn_dev.copy_(self._dyn_host, non_blocking=True)
+        for p in self.params:
+            if p.grad is not None:
+                torch.autograd.graph.increment_version(p)
+        scale = (1.0 / self.world) if grad_scale is None else grad_scale
+        _lib.check(_lib.lib.hmvae_dp_adam_step(ctypes.byref(self._peers), _lib.ptr(self.m), _lib.ptr(self.v), flat, n,
+                                               _lib.ptr(self._dyn_dev), self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                               scale, self.state.data_ptr(), ops.stream()), "dp_adam_step")
+
+    def step(self, grad_scale=None, lr=None):
+        self.advance(lr)
+        self.step_dyn(grad_scale)
+
+    def timed_out(self):
+        """True if a flag barrier ever timed out (a peer died): results are invalid."""
+        return bool(int(self.state[2].item()))
+
+    # ---- checkpoints: every rank only maintains the moments of its static share of the arena
+    def _full_moments(self):
+        lo, hi = rank_share(self.numel, self.rank, self.world)
+        m, v = torch.zeros_like(self.m), torch.zeros_like(self.v)
+        m[lo:hi] = self.m[lo:hi]
+        v[lo:hi] = self.v[lo:hi]
+        if self.world > 1:
+            dist.all_reduce(m)
+            dist.all_reduce(v)
+        return m, v
+
+    def state_dict(self):
+        m, v = self._full_moments()
+        return dict(step=self.step_count, lr=self.param_groups[0]["lr"],
+                    exp_avg=[m[o:o + p.numel()].view(p.shape).clone() for p, o in zip(self.params, self.offsets)],
+                    exp_avg_sq=[v[o:o + p.numel()].view(p.shape).clone() for p, o in zip(self.params, self.offsets)])
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.param_groups[0]["lr"] = sd.get("lr", self.lr)
+        for p, o, a, b in zip(self.params, self.offsets, sd["exp_avg"], sd["exp_avg_sq"]):
+            self.m[o:o + p.numel()].copy_(a.reshape(-1))
+            self.v[o:o + p.numel()].copy_(b.reshape(-1))

@@ -92,6 +92,34 @@ class wgrad_overlap:
         return False
 _wgrad_tc = True          # tensor-core weight gradient where the geometry is supported (False: CUDA-core wgrad)
 
+# ------------------------------------------------------------------------------------------------ gradient arena
+# dp_fused.FusedDataParallelAdam keeps all gradients in one flat, peer-mapped buffer: the weight / bias gradient kernels
+# then write straight into it (key: the parameter's data pointer, which is stable -- parameters live in an arena too).
+_grad_arena = {}
+
+
+def register_grad_buffer(param, arena, offset):
+    _grad_arena[param.data_ptr()] = (arena, int(offset), tuple(param.shape), param.numel())
+
+
+def unregister_grad_buffers(arena=None):
+    """Drops every registration (or only those that point into ``arena``)."""
+    if arena is None:
+        _grad_arena.clear()
+        return
+    for k in [k for k, e in _grad_arena.items() if e[0] is arena]:
+        del _grad_arena[k]
+
+
+def grad_buffer(param, zero=False):
+    """A fresh tensor for the gradient of ``param``: a view of the gradient arena when the parameter is registered (masked
+    conv blocks there are zero forever: nothing ever writes them), else a new allocation."""
+    e = _grad_arena.get(param.data_ptr())
+    if e is not None and e[2] == tuple(param.shape):
+        arena, off, shape, n = e
+        return arena[off:off + n].view(shape)
+    return torch.zeros_like(param) if zero else torch.empty_like(param)
+
 
 class PackedWeights:
     """Derived cache of a conv weight for the tcgen05 kernels: tf32-rounded, [block][tap][c/4][n_pad][4] for fprop and the
@@ -189,6 +217,7 @@ class _SkeletonConvFn(Function):
         else:
             check(lib.hmvae_conv_fprop(plan.handle, ptr(x), ptr(w), ptr(bias), ptr(y), b, t_in, _conv_impl, stream()), "conv_fprop")
         ctx.plan, ctx.t_in, ctx.has_bias = plan, t_in, bias is not None
+        ctx.bias_ref = bias.detach() if bias is not None else None      # identifies the bias gradient's arena slot
         ctx.wp_d = wp_d if tc_d else None
         ctx.save_for_backward(x, w, y if plan.lrelu else None)
         return y
@@ -222,16 +251,16 @@ class _SkeletonConvFn(Function):
                 side = _side_stream()
                 side.wait_stream(torch.cuda.current_stream())
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-                gb = torch.empty(plan.joints * plan.co, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+                gb = grad_buffer(ctx.bias_ref) if ctx.has_bias else None
                 ws = None
                 if _wgrad_tc and _conv_impl != IMPL_SIMT and lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in):
-                    gw = torch.zeros_like(w)                  # masked blocks are never written: they must read 0
+                    gw = grad_buffer(w, zero=True)            # masked blocks are never written: they must read 0
                     n = int(lib.hmvae_conv_wgrad_tc_workspace(plan.handle, b, t_in))
                     ws = torch.empty((n + 3) // 4, device=x.device, dtype=torch.float32)
                     check(lib.hmvae_conv_wgrad_tc(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, ptr(ws),
                                                   ws.numel() * 4, stream()), "conv_wgrad_tc")
                 else:
-                    gw = torch.empty_like(w)
+                    gw = grad_buffer(w)
                     check(lib.hmvae_conv_wgrad(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, _conv_impl, stream()),
                           "conv_wgrad")
             if side is not None:
@@ -449,6 +478,7 @@ class _LinearFn(Function):
         check(lib.hmvae_linear_fwd(ptr(x2), ptr(w), ptr(bias), ptr(y), rows, in_f, out_f, stream()), "linear_fwd")
         ctx.save_for_backward(x2, w)
         ctx.shape, ctx.has_bias = shape, bias is not None
+        ctx.bias_ref = bias.detach() if bias is not None else None
         return y.view(*shape[:-1], out_f)
 
     @staticmethod
@@ -466,8 +496,8 @@ class _LinearFn(Function):
                 side = _side_stream()
                 side.wait_stream(torch.cuda.current_stream())
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-                gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
-                gb = torch.empty(out_f, device=w.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+                gw = grad_buffer(w) if ctx.needs_input_grad[1] else None
+                gb = grad_buffer(ctx.bias_ref) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
                 check(lib.hmvae_linear_bwd(ptr(x2), ptr(w), ptr(gy2), None, ptr(gw), ptr(gb), rows, in_f, out_f, stream()), "linear_bwd(dw)")
             if side is not None:
                 _overlap["pending"].extend([x2, gy2])

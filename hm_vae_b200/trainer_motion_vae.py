@@ -10,8 +10,10 @@ Same surface: ``Trainer(cfg)``, ``gen_update(data, hp, iterations, multigpus, va
 """
 import math
 import os
+import sys
 
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.init as init
 
@@ -54,8 +56,25 @@ def get_model_list(dirname, key):
     return models[-1] if models else None
 
 
+class _NoCollective:
+    """Stand-in for BucketedAllReduce when the collective is inside the optimiser kernel (dp_fused)."""
+    fused = True
+
+    def __init__(self, world):
+        self.world, self.enabled = world, True
+
+    def begin(self):
+        pass
+
+    def finish(self):
+        pass
+
+    def allreduce_now(self):
+        pass
+
+
 class Trainer(nn.Module):
-    def __init__(self, cfg, device=None, sync_losses=True, n_buckets=4):
+    def __init__(self, cfg, device=None, sync_losses=True, n_buckets=4, dp_fused=None):
         super(Trainer, self).__init__()
         if cfg['model_name'] == "TrajectoryModel":
             self.model = TrajectoryModel(cfg, device=device)
@@ -69,6 +88,10 @@ class Trainer(nn.Module):
         self.base_lr = cfg['lr']
         self.gen_opt = None
         self._n_buckets = n_buckets
+        # data parallelism: None = fused peer-memory reduce-scatter + Adam + all-gather kernel when world > 1 (or when
+        # HMVAE_DP_FUSED=1), NCCL bucketed all-reduce + fused Adam if peer memory cannot be mapped; True / False force it
+        self._dp_fused = dp_fused
+        self.dp_mode = None
         self._sync = None
         self._graphs = {}
         self._static = None
@@ -77,8 +100,27 @@ class Trainer(nn.Module):
     def _ensure_opt(self):
         if self.gen_opt is None:
             params = [p for p in self.model.parameters() if p.requires_grad]
+            world = dist.get_world_size() if dist.is_initialized() else 1
+            fused = self._dp_fused
+            if fused is None:
+                fused = world > 1 or os.environ.get("HMVAE_DP_FUSED", "0") == "1"
+                if os.environ.get("HMVAE_DP_FUSED", "") == "0":
+                    fused = False
+            if fused:
+                try:
+                    from .dp_fused import FusedDataParallelAdam
+                    self.gen_opt = FusedDataParallelAdam(params, lr=self.base_lr, weight_decay=self.cfg['weight_decay'],
+                                                         prefer=os.environ.get("HMVAE_DP_PEER", "symm"))
+                    self._sync = _NoCollective(world)
+                    self.dp_mode = "fused_peer_memory(%s)" % self.gen_opt.arenas.backend
+                    return
+                except ops._lib.HmvaeError as exc:
+                    if self._dp_fused:
+                        raise
+                    print("hm_vae_b200: %s -- falling back to the NCCL all-reduce path" % exc, file=sys.stderr)
             self.gen_opt = ops.FusedAdam(params, lr=self.base_lr, weight_decay=self.cfg['weight_decay'])
             self._sync = BucketedAllReduce(self.model, n_buckets=self._n_buckets)
+            self.dp_mode = "nccl_bucketed_allreduce" if world > 1 else "single"
 
     def lr_at(self, iterations):
         """StepLR(step_size, gamma) (trainer_motion_vae.py:251-262); 'constant' when no policy is configured."""
@@ -130,8 +172,8 @@ class Trainer(nn.Module):
                     dst.copy_(src, non_blocking=True)
             graph.replay()
             out = static_out
-            if self._sync.world > 1:
-                # multi-GPU: the graph holds forward+backward; the NCCL all-reduce and the Adam kernel follow eagerly
+            if self._sync.world > 1 and not self._sync.fused:
+                # NCCL path: the graph holds forward+backward; the NCCL all-reduce and the Adam kernel follow eagerly
                 self._sync.allreduce_now()
                 self.gen_opt.step_dyn(grad_scale=1.0 / self._sync.world)
         else:
@@ -151,7 +193,7 @@ class Trainer(nn.Module):
         self._ensure_opt()
         dev = next(self.model.parameters()).device
         static_in = [d.to(device=dev, dtype=torch.float32).clone() if torch.is_tensor(d) else None for d in data]
-        multi = self._sync.world > 1
+        multi = self._sync.world > 1 and not self._sync.fused      # the fused peer-memory step has no NCCL call: one graph
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -202,6 +202,37 @@ int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, f
 int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const float* dyn2, float beta1, float beta2,
                         float eps, float weight_decay, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ data parallelism (train_motion_vae.py:49-53)
+ *
+ * The optimiser step fused with its collective over NVLink peer memory: every rank owns a share of the parameter elements;
+ * for those it reads the gradient from EVERY rank's gradient arena (peer loads), applies Adam with its local slice of m / v,
+ * and stores the new value into EVERY rank's parameter arena (peer stores) = reduce-scatter + sharded Adam + all-gather in one
+ * kernel, ordered by two flag barriers in peer memory (no NCCL, no host sync, CUDA-graph capturable).
+ *   peers  : device-accessible base pointers of all ranks' arenas (symmetric layout: same offset = same parameter element);
+ *            flags[q] = >= 2*world zero-initialised uint32 in rank q's memory.
+ *   ranges : HOST array [nranges][2] of element ranges [begin, end) owned by THIS rank (multiples of 4); m / v: this rank's
+ *            full-size moment arenas (only the owned ranges are touched).   dyn2: device float[2] as in hmvae_adam_step_dyn.
+ *   state  : device uint32[4], zero-initialised once: {epoch, CTA counter, timeout flag, -}.
+ * Every rank must call it the same number of times.  world == 1 degenerates to a plain fused Adam over the ranges. */
+#define HMVAE_DP_MAX_WORLD 8
+#define HMVAE_DP_MAX_RANGES 64
+typedef struct {
+  int world, rank;
+  const float* grad[HMVAE_DP_MAX_WORLD];
+  float* param[HMVAE_DP_MAX_WORLD];
+  unsigned int* flags[HMVAE_DP_MAX_WORLD];
+} hmvae_dp_peers;
+int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges, const float* dyn2,
+                       float beta1, float beta2, float eps, float weight_decay, float grad_scale, unsigned int* state,
+                       void* stream);
+/* Peer-memory plumbing over CUDA IPC (used when torch's symmetric memory is unavailable): zero-filled device allocation, its
+ * 64-byte handle, and mapping / unmapping of another process's handle. */
+int hmvae_ipc_alloc(long bytes, void** ptr);
+int hmvae_ipc_free(void* ptr);
+int hmvae_ipc_get_handle(void* ptr, unsigned char* handle64);
+int hmvae_ipc_open_handle(const unsigned char* handle64, void** ptr);
+int hmvae_ipc_close_handle(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,3 +87,73 @@ def test_bucket_order_is_reverse_of_registration():
     names = [n for b in buckets for n, _ in b]
     assert names == [n for n, _ in reversed(list(m.named_parameters()))]
     assert sum(len(b) for b in buckets) == 6 and len(buckets) <= 3
+
+
+# ------------------------------------------------------------------------------------------------ fused DP optimiser (host logic)
+def test_arena_layout_and_static_ownership():
+    from hm_vae_b200.dp_fused import ALIGN, arena_layout, merge_ranges, owned_ranges, rank_share
+
+    numels = [288 * 144 * 15, 288, 24 * 384, 24, 3, 1008, 7]
+    offs, total = arena_layout(numels)
+    assert all(o % ALIGN == 0 for o in offs) and total % ALIGN == 0
+    assert all(offs[i + 1] >= offs[i] + numels[i] for i in range(len(numels) - 1)) and total >= offs[-1] + numels[-1]
+    live = [(offs[i], offs[i] + (numels[i] + ALIGN - 1) // ALIGN * ALIGN) for i in (0, 1, 4, 6)]      # params 2, 3, 5 are dead
+    assert merge_ranges([(8, 12), (0, 4), (4, 8), (20, 24)]) == [(0, 12), (20, 24)]
+    for world in (1, 2, 3, 8):
+        shares = [rank_share(total, r, world) for r in range(world)]
+        assert shares[0][0] == 0 and shares[-1][1] == total
+        assert all(shares[r][1] == shares[r + 1][0] for r in range(world - 1))
+        covered = []
+        for r in range(world):
+            own = owned_ranges(live, r, world, total)
+            assert all(b % ALIGN == 0 and e % ALIGN == 0 and shares[r][0] <= b < e <= shares[r][1] for b, e in own)
+            covered += own
+        assert merge_ranges(covered) == merge_ranges(live)                       # union == live ...
+        assert sum(e - b for b, e in covered) == sum(e - b for b, e in merge_ranges(live))   # ... and disjoint
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hm_vae_b200.dp_fused import arena_layout, owned_ranges
+
+        # the reduce-scatter / sharded-Adam / all-gather dataflow of hmvae_dp_adam_step, emulated with gloo collectives on the
+        # host: every rank updates only its owned ranges from the SUM of all ranks' gradients, then the ranks exchange their
+        # shares; the result must equal a plain Adam step on the averaged gradient.
+        torch.manual_seed(0)
+        shapes = [(6, 5, 3), (6,), (4, 10), (3,)]
+        params = [torch.randn(*s) for s in shapes]
+        offs, total = arena_layout([p.numel() for p in params])
+        p_arena, g_arena = torch.zeros(total), torch.zeros(total)
+        for p, o in zip(params, offs):
+            p_arena[o:o + p.numel()] = p.reshape(-1)
+        torch.manual_seed(10 + rank)
+        for p, o in zip(params, offs):
+            g_arena[o:o + p.numel()] = torch.randn(p.numel())
+        live = [(o, o + (p.numel() + 3) // 4 * 4) for p, o in zip(params, offs)]
+        gsum = g_arena.clone()
+        dist.all_reduce(gsum)                                        # what the peer loads add up to
+        lr, b1, b2, eps, wd = 1e-2, 0.9, 0.999, 1e-8, 1e-4
+        new = torch.zeros(total)
+        for b, e in owned_ranges(live, rank, world, total):
+            g = gsum[b:e] / world + wd * p_arena[b:e]
+            m, v = (1 - b1) * g, (1 - b2) * g * g
+            new[b:e] = p_arena[b:e] - lr / (1 - b1) * m / (v.sqrt() / (1 - b2) ** 0.5 + eps)
+        dist.all_reduce(new)                                         # shares are disjoint: the sum is the all-gather
+        ref_p = [p.clone().requires_grad_(True) for p in params]
+        opt = torch.optim.Adam(ref_p, lr=lr, weight_decay=wd)
+        for p, o in zip(ref_p, offs):
+            p.grad = (gsum[o:o + p.numel()] / world).view(p.shape).clone()
+        opt.step()
+        ok = all(torch.allclose(new[o:o + p.numel()].view(p.shape), p.detach(), rtol=1e-5, atol=1e-7) for p, o in zip(ref_p, offs))
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_dp_dataflow_gloo_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert dict(out) == {0: True, 1: True}

@@ -421,3 +421,67 @@ def test_linear_vs_oracle(rows, i, o):
     y.backward(gy.to(DEV))
     assert rel_l2(y.detach().cpu(), torch.nn.functional.linear(x, w, b)) < 1e-5
     assert rel_l2(xm.grad.cpu(), xr.grad) < 1e-5 and rel_l2(wm.grad.cpu(), wr.grad) < 1e-5 and rel_l2(bm.grad.cpu(), br.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ fused data-parallel optimiser
+def test_dp_adam_kernel_vs_torch_single_rank():
+    """hmvae_dp_adam_step with world == 1 (no peers): arena plumbing + Adam arithmetic against torch.optim.Adam, including a
+    parameter that never receives a gradient (must stay untouched: torch skips it) and a 3-element tensor (padding)."""
+    from hm_vae_b200.dp_fused import FusedDataParallelAdam
+
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(288, 144, 15), (288,), (24, 384), (3,), (7,)]
+    ps = [torch.randn(*s, generator=gen) for s in shapes]
+    ref_p = [p.clone().requires_grad_(True) for p in ps]
+    opt_ref = torch.optim.Adam(ref_p, lr=1e-4, weight_decay=1e-4)
+    mine_p = [torch.nn.Parameter(p.clone().to(DEV)) for p in ps]
+    opt = FusedDataParallelAdam(mine_p, lr=1e-4, weight_decay=1e-4)
+    assert all(p.data_ptr() == opt.arenas.param.data_ptr() + 4 * o for p, o in zip(mine_p, opt.offsets))
+    for step in range(4):
+        gs = [torch.randn(*s, generator=gen) for s in shapes]
+        for i, (p, g) in enumerate(zip(ref_p, gs)):
+            p.grad = None if i == 2 else g.clone()
+        for i, (p, g) in enumerate(zip(mine_p, gs)):
+            if i == 2:
+                p.grad = None
+            elif i % 2 == 0:
+                buf = ops.grad_buffer(p)                      # the way the wgrad kernels deliver their result
+                buf.copy_(g.to(DEV))
+                p.grad = buf
+            else:
+                p.grad = g.clone().to(DEV)                     # a gradient autograd did not place in the arena: copied in
+        opt_ref.step()
+        opt.step()
+    assert not opt.timed_out()
+    for a, b in zip(mine_p, ref_p):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-7)
+    sd = opt.state_dict()
+    np.testing.assert_allclose(sd["exp_avg"][0].cpu().numpy(), opt_ref.state[ref_p[0]]["exp_avg"].numpy(), rtol=1e-4, atol=1e-6)
+    ops.unregister_grad_buffers()
+
+
+def test_trainer_fused_dp_matches_plain_step(smpl):
+    """Three optimisation steps of the len8 model through Trainer with the fused arena optimiser (forced on one GPU) and with
+    the multi-tensor Adam: same losses, same parameters (the gradient kernels write straight into the arena)."""
+    from hm_vae_b200.trainer_motion_vae import Trainer
+
+    hp = dict(HP8, model_name="TwoHierSAVAEModel", init="kaiming", lr=1e-4, weight_decay=1e-4, lr_policy="constant")
+    parents, off = smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])
+    batch = O.synthetic_batch(4, 8, parents, off, seed=3)
+    data = (batch["seq_rot_6d"].to(DEV), batch["seq_rot_mat"].to(DEV))
+    results = []
+    for fused in (False, True):
+        torch.manual_seed(11)
+        tr = Trainer(dict(hp), device=DEV, sync_losses=False, dp_fused=fused).to(DEV)
+        torch.manual_seed(12)
+        losses = [float(tr.gen_update(data, hp, 0)[0]) for _ in range(3)]
+        if fused:
+            assert tr.dp_mode.startswith("fused_peer_memory") and not tr.gen_opt.timed_out()
+            live = [p for p in tr.gen_opt.params if p.grad is not None]
+            assert live and all(p.grad.data_ptr() == tr.gen_opt.arenas.grad.data_ptr() + 4 * o
+                                for p, o in zip(tr.gen_opt.params, tr.gen_opt.offsets) if p.grad is not None)
+        results.append((losses, {k: v.detach().cpu().clone() for k, v in tr.model.named_parameters()}))
+        ops.unregister_grad_buffers()
+    np.testing.assert_allclose(results[0][0], results[1][0], rtol=1e-5)
+    for k in results[0][1]:
+        np.testing.assert_allclose(results[1][1][k].numpy(), results[0][1][k].numpy(), rtol=1e-4, atol=1e-6, err_msg=k)

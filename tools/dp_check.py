@@ -1,0 +1,52 @@
+"""2+ GPU check of the fused peer-memory data-parallel step (run under torchrun):
+   1. the same 3 optimisation steps through the fused kernel and through NCCL all-reduce + multi-tensor Adam must give the
+      same parameters on every rank;
+   2. prints which peer-memory backend was used and whether a flag barrier ever timed out."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import yaml  # noqa: E402
+
+from hm_vae_b200 import ddp, ops  # noqa: E402
+from hm_vae_b200.trainer_motion_vae import Trainer  # noqa: E402
+
+rank, world, local = ddp.init_from_env("nccl")
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+hp = yaml.safe_load(open(os.path.join(os.path.dirname(__file__), "..", "configs", "len64_no_aug_hm_vae.yaml")))
+bs, T = 8, hp["train_seq_len"]
+g = torch.Generator().manual_seed(100 + rank)
+x6 = torch.randn(bs, T, 24, 6, generator=g).to(dev)
+rot = ops.rot6d_to_rotmat(x6)
+data = (torch.stack((rot[..., 0], rot[..., 1]), dim=-2).reshape(bs, T, -1).contiguous(), rot.reshape(bs, T, -1).contiguous())
+out = {}
+for fused in (False, True):
+    torch.manual_seed(0)
+    tr = Trainer(dict(hp), device=dev, sync_losses=False, dp_fused=fused).to(dev)
+    ddp.broadcast_parameters(tr.model)
+    torch.manual_seed(50 + rank)
+    losses = [float(tr.gen_update(data, hp, 0)[0]) for _ in range(3)]
+    torch.cuda.synchronize()
+    out[fused] = {k: v.detach().clone() for k, v in tr.model.named_parameters()}
+    if fused:
+        print("rank %d: dp_mode %s timed_out %s losses %s" % (rank, tr.dp_mode, tr.gen_opt.timed_out(), losses), flush=True)
+    else:
+        print("rank %d: dp_mode %s losses %s" % (rank, tr.dp_mode, losses), flush=True)
+    ops.unregister_grad_buffers()
+worst = 0.0
+for k in out[False]:
+    a, b = out[True][k].double(), out[False][k].double()
+    worst = max(worst, float((a - b).abs().max()))          # absolute: zero-initialised biases are O(lr) after 3 steps
+# every rank must hold identical parameters after the fused steps
+chk = torch.stack([v.double().sum() for v in out[True].values()]).sum().reshape(1)
+gathered = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(gathered, chk)
+same = all(float(t) == float(gathered[0]) for t in gathered)
+print("rank %d: fused vs nccl worst abs parameter diff %.3e (lr 1e-4, 3 steps); ranks identical: %s" % (rank, worst, same), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if (worst < 2e-5 and same) else 1)
