@@ -88,8 +88,9 @@ class Trainer(nn.Module):
         self.base_lr = cfg['lr']
         self.gen_opt = None
         self._n_buckets = n_buckets
-        # data parallelism: None = fused peer-memory reduce-scatter + Adam + all-gather kernel when world > 1 (or when
-        # HMVAE_DP_FUSED=1), NCCL bucketed all-reduce + fused Adam if peer memory cannot be mapped; True / False force it
+        # optimiser / data parallelism: None = flat-arena Adam whose kernel is also the collective (peer-memory reduce-scatter
+        # + Adam + all-gather when world > 1), falling back to NCCL bucketed all-reduce + multi-tensor Adam if peer memory cannot
+        # be mapped (or HMVAE_DP_FUSED=0); True / False force one or the other
         self._dp_fused = dp_fused
         self.dp_mode = None
         self._sync = None
@@ -103,9 +104,7 @@ class Trainer(nn.Module):
             world = dist.get_world_size() if dist.is_initialized() else 1
             fused = self._dp_fused
             if fused is None:
-                fused = world > 1 or os.environ.get("HMVAE_DP_FUSED", "0") == "1"
-                if os.environ.get("HMVAE_DP_FUSED", "") == "0":
-                    fused = False
+                fused = os.environ.get("HMVAE_DP_FUSED", "1") != "0"
             if fused:
                 try:
                     from .dp_fused import FusedDataParallelAdam
