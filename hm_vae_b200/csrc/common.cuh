@@ -40,8 +40,33 @@ inline int check_launch(const char* what) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int num_sms();
+bool pdl_enabled();   // HMVAE_PDL=1 (default off): programmatic dependent launch between consecutive kernels of a stream
+
+// Launch with the "programmatic stream serialization" attribute: the kernel may be scheduled while its predecessor in the
+// stream is still running; it runs its prologue (barrier init, TMEM allocation, constant tables) and then blocks in pdl_wait()
+// until the predecessor has completed and flushed.  A step here is ~100 dependent, mostly latency-bound launches, so hiding the
+// launch latency + prologue of each one matters.  RULE: every kernel launched through this helper calls pdl_wait() on every
+// control path before it touches global memory that another kernel writes or reads (completion must stay transitive).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------- device helpers
+// programmatic dependent launch: let the next kernel of the stream start its prologue / wait for the previous one to finish
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -1,11 +1,24 @@
 // C ABI for the skeleton-aware conv: plan construction (index tables) and implementation dispatch.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "conv_common.cuh"
 
 namespace hmvae {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    // Measured on B200 (profiles/r01_summary_v3.md): back-to-back eager launches gain ~12 % device time, but inside the step's
+    // CUDA graph early-launched 200 KB-smem CTAs sit on SMs the other stream's kernels want (1.217 vs 1.205 ms) => opt-in.
+    const char* e = getenv("HMVAE_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on != 0;
+}
 
 int num_sms() {
   static int cached = 0;

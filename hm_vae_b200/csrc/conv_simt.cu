@@ -290,6 +290,8 @@ __global__ void __launch_bounds__(CV_TPB) conv_wgrad_kernel(ConvArgs a, const fl
 // dsrc[b, sj*ci + c, v] = sum_{n: src[n] = sj} upsample2^T(dxin[b, n*ci + c, :])[v]  (* lrelu'(src_act))
 __global__ void conv_prologue_bwd_kernel(ConvArgs a, const float* __restrict__ dxin, const float* __restrict__ src_act,
                                          float* __restrict__ dsrc, int B, int T, long total) {
+  pdl_trigger();
+  pdl_wait();
   const int Ts = a.upsample ? T / 2 : T;
   const int Cin = a.J * a.ci;
   for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
@@ -429,7 +431,6 @@ extern "C" int hmvae_conv_prologue_bwd(const hmvae_conv_plan* plan, const float*
   const long total = (long)batch * a.src_J * a.ci * Ts;
   if (total <= 0) return 0;
   long blocks = (total + 255) / 256, cap = (long)num_sms() * 16;
-  conv_prologue_bwd_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a, dxin, src_act, dsrc,
-                                                                                             batch, t_in, total);
+  launch_pdl(conv_prologue_bwd_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, (cudaStream_t)stream, a, dxin, src_act, dsrc, batch, t_in, total);
   return check_launch("conv_prologue_bwd");
 }

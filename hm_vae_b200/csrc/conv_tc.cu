@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(128) conv_pack_kernel(ConvArgs a, const float*
                                                         float4* __restrict__ wp_d, const TcPk* __restrict__ pk, int npad_f,
                                                         int kc_f, int npad_d, int kc_d) {
   extern __shared__ float rows[];               // [4][ci*K]
+  pdl_trigger();
+  pdl_wait();
   const int Cin = a.J * a.ci;
   const int run = a.ci * a.K;
   const int no4 = (a.co + 3) / 4;
@@ -156,6 +158,8 @@ __global__ void __launch_bounds__(128) conv_pack_kernel(ConvArgs a, const float*
 // astage[mt][n][cb][h][rows_alloc][4]  (cb = KC-channel block, h = 16-byte chunk inside the block)
 __global__ void __launch_bounds__(256) conv_tc_prep_kernel(TcArgs p, const float* __restrict__ src,
                                                            const float* __restrict__ yact, float4* __restrict__ astage) {
+  pdl_trigger();
+  pdl_wait();
   const ConvArgs& a = p.a;
   const int Tq = p.T + 2 * a.p;
   const int tfill = (p.mode == 0) ? Tq : (Tq + a.K - 1);
@@ -224,6 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) TcWork work;
 
+  pdl_trigger();
   const ConvArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x;
@@ -269,6 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();       // prologue done (barriers, TMEM, work table = plan constants): now wait for the producer of astage / wp
   const uint32_t slot_u = (uint32_t)p.n_pad;                 // 16-byte units per slot inside one (tap, chunk) row block
   const int si_beg = blockIdx.z * p.split_len, si_end = si_beg + p.split_len;
 
@@ -453,6 +459,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
 // ---------------------------------------------------------------------------------------------- split-K finish
 __global__ void conv_tc_finish_kernel(TcArgs p, const float* __restrict__ part, const float* __restrict__ bias,
                                       float* __restrict__ dst) {
+  pdl_trigger();
+  pdl_wait();
   const ConvArgs& a = p.a;
   const int Tr = (p.mode == 0) ? p.T_out : p.T;
   const int C = a.J * p.n_real;
@@ -723,8 +731,8 @@ int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* w
   if ((wp_f && !aligned16(wp_f)) || (wp_d && !aligned16(wp_d))) return fail_arg("conv_pack_weights: buffers must be 16-byte aligned");
   const size_t smem = (size_t)4 * a.ci * a.K * 4;
   if (smem > 48 * 1024) HMVAE_CUDA(cudaFuncSetAttribute(conv_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv_pack_kernel<<<a.nnz * ((a.co + 3) / 4), 128, smem, st>>>(a, w, reinterpret_cast<float4*>(wp_f), reinterpret_cast<float4*>(wp_d),
-                                                               LL->dev_pk, LL->m[0].n_pad, LL->m[0].KC, LL->m[1].n_pad, LL->m[1].KC);
+  launch_pdl(conv_pack_kernel, dim3(a.nnz * ((a.co + 3) / 4)), dim3(128), smem, st, a, w, reinterpret_cast<float4*>(wp_f),
+             reinterpret_cast<float4*>(wp_d), LL->dev_pk, LL->m[0].n_pad, LL->m[0].KC, LL->m[1].n_pad, LL->m[1].KC);
   return check_launch("conv_pack");
 }
 
@@ -740,20 +748,21 @@ int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, cons
     const int Tq = T + 2 * p.a.p;
     const long items = (long)p.mtiles * p.a.J * (p.ck_pad / 4) * p.Bt * (mode == 0 ? Tq : Tq + p.a.K - 1);
     long blocks = (items + 255) / 256, cap = (long)num_sms() * 8;
-    conv_tc_prep_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, src, yact, reinterpret_cast<float4*>(workspace));
+    launch_pdl(conv_tc_prep_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, src, yact,
+               reinterpret_cast<float4*>(workspace));
     int rc = check_launch("conv_tc_prep");
     if (rc) return rc;
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.mtiles, (p.a.J + p.GJ - 1) / p.GJ, p.splits);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, reinterpret_cast<const unsigned char*>(workspace), wp, bias,
-                                                 p.splits > 1 ? part : dst);
+  launch_pdl(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, p, reinterpret_cast<const unsigned char*>(workspace), wp, bias,
+             p.splits > 1 ? part : dst);
   int rc = check_launch(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
   if (rc || p.splits <= 1) return rc;
   const long per = (long)p.B * p.a.J * p.n_real * (mode == 0 ? p.T_out : p.T);
   long blocks = (per + 255) / 256, cap = (long)num_sms() * 8;
-  conv_tc_finish_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, part, bias, dst);
+  launch_pdl(conv_tc_finish_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, (const float*)part, bias, dst);
   return check_launch("conv_tc_finish");
 }
 

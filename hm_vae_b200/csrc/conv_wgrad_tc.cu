@@ -89,6 +89,8 @@ __device__ __host__ __forceinline__ void wg_window(int s, int k0, int L, int pha
 __global__ void __launch_bounds__(256) conv_wgrad_prep_kernel(WgArgs p, const float* __restrict__ x,
                                                               const float* __restrict__ dy, const float* __restrict__ yact,
                                                               float4* __restrict__ dyw, float4* __restrict__ xw) {
+  pdl_trigger();
+  pdl_wait();
   const ConvArgs& a = p.a;
   const int nst = p.mtiles * p.nwin;
   const long n_dy = (long)nst * p.slabs * (p.Rd / 4) * 128;
@@ -156,6 +158,8 @@ __global__ void __launch_bounds__(128) conv_bias_grad_kernel(ConvArgs a, const f
                                                              const float* __restrict__ yact, float* __restrict__ db, int B,
                                                              int T_out, int accumulate) {
   __shared__ float red[4];
+  pdl_trigger();
+  pdl_wait();
   const int ch = blockIdx.x;
   const int j = ch / a.co, o = ch % a.co;
   float acc = 0.f;
@@ -194,9 +198,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
   __shared__ uint64_t full_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], accum_bar;
   __shared__ uint32_t tmem_base_s;
 
+  pdl_trigger();
   const ConvArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const WgItem item = p.items[blockIdx.x];
+  const WgItem item = p.items[blockIdx.x];          // plan constant
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -215,6 +220,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();       // prologue done: now wait for the staging kernel
   const int nst_all = p.mtiles * p.nwin;
   const int st_beg = blockIdx.y * p.plen;
   const int st_end = (st_beg + p.plen < nst_all) ? st_beg + p.plen : nst_all;
@@ -350,6 +356,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(WgArgs p, 
 // ---------------------------------------------------------------------------------------------- split reduce
 // dw[e] (= or +=) sum over splits of part[s][e], for unmasked entries only, in a fixed order (deterministic)
 __global__ void conv_wgrad_reduce_kernel(WgArgs p, const float* __restrict__ part, float* __restrict__ dw, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const ConvArgs& a = p.a;
   const long per_row = (long)a.ci * a.K;
   const long total = (long)a.nnz * a.co * per_row;
@@ -547,14 +555,14 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
   {
     const long items = (wg_dy_bytes(p) + wg_x_bytes(p)) / 16;
     long blocks = (items + 255) / 256, cap = (long)num_sms() * 8;
-    conv_wgrad_prep_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, x, dy, yact, reinterpret_cast<float4*>(dyw),
-                                                                             reinterpret_cast<float4*>(xw));
+    launch_pdl(conv_wgrad_prep_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, x, dy, yact,
+               reinterpret_cast<float4*>(dyw), reinterpret_cast<float4*>(xw));
     int rc = check_launch("conv_wgrad_prep");
     if (rc) return rc;
   }
   if (dbias) {
     const int ch = p.a.J * p.a.co;
-    conv_bias_grad_kernel<<<ch, 128, 0, st>>>(p.a, dy, yact, dbias, B, p.T_out, accumulate);
+    launch_pdl(conv_bias_grad_kernel, dim3(ch), dim3(128), 0, st, p.a, dy, yact, dbias, B, p.T_out, accumulate);
     int rc = check_launch("conv_bias_grad");
     if (rc) return rc;
   }
@@ -565,12 +573,13 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
   HMVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* part = reinterpret_cast<float*>(xw + wg_x_bytes(p));
   dim3 grid(p.nitems, p.psplits);
-  conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(p, dyw, xw, p.psplits > 1 ? part : dw, accumulate);
+  launch_pdl(conv_wgrad_tc_kernel, grid, dim3(WG_THREADS), smem, st, p, (const unsigned char*)dyw, (const unsigned char*)xw,
+             p.psplits > 1 ? part : dw, accumulate);
   int rc = check_launch("conv_wgrad_tc");
   if (rc || p.psplits <= 1) return rc;
   const long total = (long)p.a.nnz * p.a.co * p.a.ci * p.a.K;
   long blocks = (total + 255) / 256, cap = (long)num_sms() * 8;
-  conv_wgrad_reduce_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, part, dw, accumulate);
+  launch_pdl(conv_wgrad_reduce_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, (const float*)part, dw, accumulate);
   return check_launch("conv_wgrad_reduce");
 }
 

@@ -62,6 +62,8 @@ __device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int
 __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restrict__ m, float* __restrict__ v,
                                                       const float* __restrict__ dyn2, float beta1, float beta2, float eps,
                                                       float wd, float gscale, unsigned int* __restrict__ state) {
+  pdl_trigger();
+  pdl_wait();
   // state[0] = epoch of the last completed call, state[1] = CTAs done in this call, state[2] = timeout flag
   __shared__ unsigned int s_epoch;
   const int W = A.world, R = A.rank;
@@ -157,7 +159,7 @@ extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* 
   const long cap = (long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  dp_adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, m, v, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state);
+  launch_pdl(dp_adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state);
   return check_launch("dp_adam_step");
 }
 

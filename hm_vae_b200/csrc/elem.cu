@@ -24,6 +24,8 @@ struct EdgeTab {
 // ------------------------------------------------------------------------------------------------ pool / unpool
 __global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int E_in, int E_out, int c, int T,
                                 long total, EdgeTab tab, int lrelu) {
+  pdl_trigger();
+  pdl_wait();
   for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
     const int t = (int)(o % T);
     long r = o / T;
@@ -40,6 +42,8 @@ __global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__
 
 __global__ void pool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
                                 int E_in, int E_out, int c, int T, long total, EdgeTab tab, int lrelu) {
+  pdl_trigger();
+  pdl_wait();
   for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
     const int t = (int)(o % T);
     long r = o / T;
@@ -120,6 +124,8 @@ __global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __re
 
 // [B, C, T] -> [B, T, C] through a padded 32x32 smem tile
 __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int T) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const long b = blockIdx.z;
   const int c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
@@ -153,6 +159,8 @@ __device__ __forceinline__ float block_sum(float v) {
 __global__ void __launch_bounds__(1024) latent_fwd_kernel(const float* __restrict__ dist, const float* __restrict__ eps,
                                                           float* __restrict__ z, float* __restrict__ kl_out, long rows,
                                                           int d) {
+  pdl_trigger();
+  pdl_wait();
   float acc = 0.f;
   const long total = rows * d;
   for (long o = threadIdx.x; o < total; o += blockDim.x) {
@@ -169,6 +177,8 @@ __global__ void __launch_bounds__(1024) latent_fwd_kernel(const float* __restric
 __global__ void latent_bwd_kernel(const float* __restrict__ dist, const float* __restrict__ eps,
                                   const float* __restrict__ dz, const float* __restrict__ dkl,
                                   float* __restrict__ ddist, long rows, int d, float kl_scale) {
+  pdl_trigger();
+  pdl_wait();
   const long total = rows * d;
   if (dkl) kl_scale *= dkl[0];
   for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
@@ -189,6 +199,8 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dist, const float* _
 // (ready for the next step).  n <= 8.
 struct LossCoef { float scale[8], w[8], wk[8]; int n; };
 __global__ void loss_finalize_kernel(float* __restrict__ acc, float* __restrict__ out, LossCoef c) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0) {
     float total = 0.f, kl = 0.f;
     for (int i = 0; i < c.n; ++i) {
@@ -279,6 +291,8 @@ struct AdamPack {
 __global__ void __launch_bounds__(EW_TPB) adam_kernel(AdamPack pack, float lr_over_bc1, float inv_sqrt_bc2, float beta1,
                                                       float beta2, float eps, float wd, float gscale,
                                                       const float* __restrict__ dyn2) {
+  pdl_trigger();
+  pdl_wait();
   if (dyn2) {
     lr_over_bc1 = dyn2[0];
     inv_sqrt_bc2 = dyn2[1];
@@ -341,7 +355,7 @@ extern "C" int hmvae_pool_fwd(const float* x, float* y, int batch, int in_edges,
   if (rc) return rc;
   const long total = (long)batch * out_edges * c * t;
   if (total <= 0) return 0;
-  pool_fwd_kernel<<<ew_grid(total), EW_TPB, 0, (cudaStream_t)stream>>>(x, y, in_edges, out_edges, c, t, total, tab, lrelu);
+  launch_pdl(pool_fwd_kernel, dim3(ew_grid(total)), dim3(EW_TPB), 0, (cudaStream_t)stream, x, y, in_edges, out_edges, c, t, total, tab, lrelu);
   return check_launch("pool_fwd");
 }
 
@@ -353,7 +367,7 @@ extern "C" int hmvae_pool_bwd(const float* dy, const float* y, float* dx, int ba
   if (rc) return rc;
   const long total = (long)batch * in_edges * c * t;
   if (total <= 0) return 0;
-  pool_bwd_kernel<<<ew_grid(total), EW_TPB, 0, (cudaStream_t)stream>>>(dy, y, dx, in_edges, out_edges, c, t, total, tab, lrelu);
+  launch_pdl(pool_bwd_kernel, dim3(ew_grid(total)), dim3(EW_TPB), 0, (cudaStream_t)stream, dy, y, dx, in_edges, out_edges, c, t, total, tab, lrelu);
   return check_launch("pool_bwd");
 }
 
@@ -428,7 +442,7 @@ extern "C" int hmvae_transpose_ct(const float* x, float* y, int batch, int c, in
   if (batch <= 0 || c <= 0 || t <= 0) return 0;
   if (batch > 65535) return fail_arg("transpose_ct: batch > 65535");
   dim3 grid((t + 31) / 32, (c + 31) / 32, batch), block(32, 8);
-  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, c, t);
+  launch_pdl(transpose_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, x, y, c, t);
   return check_launch("transpose_ct");
 }
 
@@ -436,14 +450,14 @@ extern "C" int hmvae_latent_fwd(const float* dist, const float* eps, float* z, f
                                 void* stream) {
   if (!dist) return fail_arg("latent_fwd: null pointer");
   if (rows * d <= 0) return 0;
-  latent_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dist, eps, z, kl_out, rows, d);
+  launch_pdl(latent_fwd_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, dist, eps, z, kl_out, rows, d);
   return check_launch("latent_fwd");
 }
 extern "C" int hmvae_latent_bwd(const float* dist, const float* eps, const float* dz, const float* dkl, float* ddist,
                                 long rows, int d, float kl_scale, void* stream) {
   if (!dist || !ddist) return fail_arg("latent_bwd: null pointer");
   if (rows * d <= 0) return 0;
-  latent_bwd_kernel<<<ew_grid(rows * d), EW_TPB, 0, (cudaStream_t)stream>>>(dist, eps, dz, dkl, ddist, rows, d, kl_scale);
+  launch_pdl(latent_bwd_kernel, dim3(ew_grid(rows * d)), dim3(EW_TPB), 0, (cudaStream_t)stream, dist, eps, dz, dkl, ddist, rows, d, kl_scale);
   return check_launch("latent_bwd");
 }
 extern "C" int hmvae_loss_finalize(float* acc, float* out, const float* scale, const float* w, const float* wk, int n,
@@ -452,7 +466,7 @@ extern "C" int hmvae_loss_finalize(float* acc, float* out, const float* scale, c
   LossCoef c;
   for (int i = 0; i < 8; ++i) { c.scale[i] = i < n ? scale[i] : 0.f; c.w[i] = i < n ? w[i] : 0.f; c.wk[i] = i < n ? wk[i] : 0.f; }
   c.n = n;
-  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, out, c);
+  launch_pdl(loss_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, acc, out, c);
   return check_launch("loss_finalize");
 }
 
@@ -498,8 +512,7 @@ static int adam_launch(const hmvae_adam_tensor* tensors, int n_tensors, float lr
     if (bx < 1) bx = 1;
     if (bx > cap) bx = cap;
     dim3 grid((unsigned)bx, (unsigned)cnt);
-    adam_kernel<<<grid, EW_TPB, 0, (cudaStream_t)stream>>>(pack, lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, weight_decay,
-                                                          grad_scale, dyn2);
+    launch_pdl(adam_kernel, dim3(grid), dim3(EW_TPB), 0, (cudaStream_t)stream, pack, lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, weight_decay, grad_scale, dyn2);
     int rc = check_launch("adam_step");
     if (rc) return rc;
   }

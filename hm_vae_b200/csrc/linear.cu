@@ -11,6 +11,8 @@ constexpr int NT_OB = 8;
 __global__ void __launch_bounds__(256) linear_nt_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y, int R, int I,
                                                         int O) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int ogroups = (O + NT_OB - 1) / NT_OB;
   const long wid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(256) linear_nt_kernel(const float* __restrict_
 // ---- dx[r, i] = sum_o dy[r, o] * w[o, i]      (short reduction, wide contiguous output): one thread per output
 __global__ void __launch_bounds__(256) linear_nn_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                         float* __restrict__ dx, int R, int I, int O) {
+  pdl_trigger();
+  pdl_wait();
   const long e = (long)blockIdx.x * 256 + threadIdx.x;
   if (e >= (long)R * I) return;
   const int r = (int)(e / I), i = (int)(e % I);
@@ -47,11 +51,31 @@ __global__ void __launch_bounds__(256) linear_nn_kernel(const float* __restrict_
   dx[e] = acc0 + acc1;
 }
 
+// ---- same product when the reduction is LONG and the output narrow (decoder heads: O = 384, I = 12 / 24): one warp per
+// output, lanes stride over o (dy coalesced, the 18 KB weight matrix stays in L1), warp reduction.  The one-thread-per-output
+// kernel above ran 384 dependent iterations on 21 CTAs (35 us).
+__global__ void __launch_bounds__(256) linear_nn_wide_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                             float* __restrict__ dx, int R, int I, int O) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long wid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wid >= (long)R * I) return;
+  const int r = (int)(wid / I), i = (int)(wid % I);
+  const float* g = dy + (long)r * O;
+  float acc = 0.f;
+  for (int o = lane; o < O; o += 32) acc += g[o] * w[(long)o * I + i];
+  acc = warp_sum(acc);
+  if (lane == 0) dx[wid] = acc;
+}
+
 // ---- C[a, b] = sum_r P[r, a] * Q[r, b]      (long reduction over rows; Q wide, P narrow)
 // CTA = 8 a x 32 b outputs; the 8 warps split the rows, partial sums are combined through shared memory in a fixed order.
 // out index = transpose ? b*A + a : a*Bn + b.
 __global__ void __launch_bounds__(256) linear_tn_kernel(const float* __restrict__ P, const float* __restrict__ Q,
                                                         float* __restrict__ out, int R, int A, int Bn, int transpose) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][8][33];
   const int lane = threadIdx.x & 31, ks = threadIdx.x >> 5;
   const int b = blockIdx.x * 32 + lane, a0 = blockIdx.y * 8;
@@ -82,6 +106,8 @@ __global__ void __launch_bounds__(256) linear_tn_kernel(const float* __restrict_
 
 // out[n] = sum_m x[m, n]   (x row-major [M, N]); one warp per 32 columns chunk, fixed order
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -107,7 +133,7 @@ extern "C" int hmvae_linear_fwd(const float* x, const float* w, const float* bia
   if (!x || !w || !y) return fail_arg("linear_fwd: null pointer");
   if (rows <= 0 || in_f <= 0 || out_f <= 0) return 0;
   const long warps = (long)rows * ((out_f + NT_OB - 1) / NT_OB);
-  linear_nt_kernel<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, rows, in_f, out_f);
+  launch_pdl(linear_nt_kernel, dim3((int)((warps + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, x, w, bias, y, rows, in_f, out_f);
   return check_launch("linear_fwd");
 }
 
@@ -118,7 +144,10 @@ extern "C" int hmvae_linear_bwd(const float* x, const float* w, const float* dy,
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {
     const long total = (long)rows * in_f;
-    linear_nn_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(dy, w, dx, rows, in_f, out_f);
+    if (out_f >= 128 && total <= (1L << 20))
+      launch_pdl(linear_nn_wide_kernel, dim3((int)((total + 7) / 8)), dim3(256), 0, st, dy, w, dx, rows, in_f, out_f);
+    else
+      launch_pdl(linear_nn_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, dy, w, dx, rows, in_f, out_f);
     int rc = check_launch("linear_bwd(dx)");
     if (rc) return rc;
   }
@@ -126,16 +155,16 @@ extern "C" int hmvae_linear_bwd(const float* x, const float* w, const float* dy,
     // dw[o, i] = sum_r dy[r, o] x[r, i]: the wider of the two operands is read coalesced
     if (in_f >= out_f) {
       dim3 grid((in_f + 31) / 32, (out_f + 7) / 8);
-      linear_tn_kernel<<<grid, 256, 0, st>>>(dy, x, dw, rows, out_f, in_f, 0);
+      launch_pdl(linear_tn_kernel, dim3(grid), dim3(256), 0, st, dy, x, dw, rows, out_f, in_f, 0);
     } else {
       dim3 grid((out_f + 31) / 32, (in_f + 7) / 8);
-      linear_tn_kernel<<<grid, 256, 0, st>>>(x, dy, dw, rows, in_f, out_f, 1);
+      launch_pdl(linear_tn_kernel, dim3(grid), dim3(256), 0, st, x, dy, dw, rows, in_f, out_f, 1);
     }
     int rc = check_launch("linear_bwd(dw)");
     if (rc) return rc;
   }
   if (db) {
-    colsum_kernel<<<(out_f + 31) / 32, 256, 0, st>>>(dy, db, rows, out_f);
+    launch_pdl(colsum_kernel, dim3((out_f + 31) / 32), dim3(256), 0, st, dy, db, rows, out_f);
     int rc = check_launch("linear_bwd(db)");
     if (rc) return rc;
   }

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(32 * RC_FR) recon_par_kernel(const float* __re
                                                                float srot, float spos, float* __restrict__ losses,
                                                                float* __restrict__ dx6, float* __restrict__ pos_out,
                                                                float* __restrict__ gtpos_out, ParTree tr) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_tile[NCW ? 6 * FK_MAX_J * RC_TP : 1];
   __shared__ float s_R[RC_FR][FK_MAX_J][9], s_Rt[RC_FR][FK_MAX_J][9], s_G[RC_FR][FK_MAX_J][9], s_S[RC_FR][FK_MAX_J][3];
   __shared__ float s_off[FK_MAX_J * 3];
@@ -215,8 +217,7 @@ static int launch_recon_par(const float* x6p, const float* gt6, const float* gtR
                             const ParTree& tr, cudaStream_t st) {
   const long tiles = ((long)B * T + RC_FR - 1) / RC_FR;
   if (tiles > 0x7fffffffL) return fail_arg("recon_fwdbwd: too many frames");
-  recon_par_kernel<NCW><<<(int)tiles, 32 * RC_FR, 0, st>>>(x6p, gt6, gtR, offsets, B, T, s6, srot, spos, losses, dx6, pos_out,
-                                                          gtpos_out, tr);
+  launch_pdl(recon_par_kernel<NCW>, dim3((int)tiles), dim3(32 * RC_FR), 0, st, x6p, gt6, gtR, offsets, B, T, s6, srot, spos, losses, dx6, pos_out, gtpos_out, tr);
   return check_launch("recon_fwdbwd");
 }
 
