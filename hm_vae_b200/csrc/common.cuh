@@ -40,6 +40,7 @@ inline int check_launch(const char* what) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int num_sms();
+int env_int(const char* name, int dflt);   // tuning knobs (read once per call site is fine: geometry is memoised)
 bool pdl_enabled();   // HMVAE_PDL=1 (default off): programmatic dependent launch between consecutive kernels of a stream
 
 // Launch with the "programmatic stream serialization" attribute: the kernel may be scheduled while its predecessor in the

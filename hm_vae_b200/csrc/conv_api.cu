@@ -9,6 +9,11 @@ namespace hmvae {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {

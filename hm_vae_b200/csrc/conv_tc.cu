@@ -679,11 +679,18 @@ static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mod
   p.mtiles = (B + p.Bt - 1) / p.Bt;
   p.a_bytes = (p.KC / 4) * p.rows_alloc * 16;
   p.stage_bytes = rup(p.a_bytes + L.nbmax * a.K * (p.KC / 4) * p.n_pad * 16, 128);
-  const int budget = 208 * 1024;
+  const int budget = env_int("HMVAE_TC_SMEM_KB", 208) * 1024;     // dynamic shared memory per CTA (stage ring)
   p.stages = budget / p.stage_bytes;
-  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
-  const int epi = p.GJ * p.n_real * 128 * 4;
-  if (p.stages < 2 || epi > p.stages * p.stage_bytes) return false;
+  {
+    // Measured (profiles/r01_summary_v3.md): the K loop of a CTA is only 3-10 stages long at B=32, so a deep ring buys nothing,
+    // while 2 stages (50-120 KB) let two CTAs -- of this kernel, or of the weight-gradient kernel running on the other stream --
+    // share an SM: 1.197 -> 1.112 ms per step.
+    int cap = env_int("HMVAE_TC_STAGES", 2);
+    if (cap > TC_MAX_STAGES) cap = TC_MAX_STAGES;
+    if (cap < 2) cap = 2;
+    if (p.stages > cap) p.stages = cap;
+  }
+  if (p.stages < 2) return false;
   int cols = p.GJ * p.n_pad, pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   if (pow2 > 512) return false;
@@ -753,7 +760,10 @@ int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, cons
     int rc = check_launch("conv_tc_prep");
     if (rc) return rc;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  size_t smem = (size_t)p.stages * p.stage_bytes;
+  const size_t epi = (size_t)p.GJ * p.n_real * 128 * 4;      // the epilogue's transpose buffer reuses the stage ring
+  if (epi > smem) smem = epi;
+  smem += 1024;
   HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.mtiles, (p.a.J + p.GJ - 1) / p.GJ, p.splits);
   launch_pdl(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, p, reinterpret_cast<const unsigned char*>(workspace), wp, bias,

@@ -402,7 +402,11 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
   p.slabs = (p.dy_chunks + 31) / 32;
   p.nphase = a.s;
   // taps per group: L * Nw accumulator columns <= 512
-  p.Lmax = 512 / p.Nw;
+  // accumulator columns per CTA.  Measured: 128 columns (one tap of a 128-column window per CTA => 15x more, shorter CTAs that
+  // co-reside with the dgrad kernels of the other stream) beats 256 / 384 / 512: 0.971 / 0.997 / 1.063 / 1.112 ms per step.
+  const int tmem_cap = env_int("HMVAE_WG_TMEM_COLS", 128);
+  p.Lmax = tmem_cap / p.Nw;
+  if (p.Lmax < 1) p.Lmax = 1;
   if (p.Lmax > 16) p.Lmax = 16;                     // epilogue transpose tile: 128 x (16 * L + 1) floats <= 132 KB
   if (p.Lmax > a.K) p.Lmax = a.K;
   p.TG = (a.K + p.Lmax - 1) / p.Lmax;
@@ -434,7 +438,7 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
     p.a_bytes = (p.Rd / 4) * 128 * 16;
     p.b_bytes = p.nphase * (p.Rx / 4) * p.Nw * 16;
     p.stage_bytes = rup(p.a_bytes + p.b_bytes, 128);
-    p.stages = (200 * 1024) / p.stage_bytes;
+    p.stages = (env_int("HMVAE_WG_SMEM_KB", 200) * 1024) / p.stage_bytes;
   };
   int bt0 = rup(64 / p.Tw > 4 ? 64 / p.Tw : 4, 4);
   if (bt0 > rup(B, 4)) bt0 = rup(B, 4);
@@ -443,7 +447,12 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
   for (int bt = bt0 - 4; p.stages < 3 && bt >= 4; bt -= 4)
     if ((p.Tw * bt) % 8 == 0) size_stage(bt);
   p.mtiles = (B + p.Bt - 1) / p.Bt;
-  if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+  {
+    int cap = env_int("HMVAE_WG_STAGES", 2);
+    if (cap > WG_MAX_STAGES) cap = WG_MAX_STAGES;
+    if (cap < 2) cap = 2;
+    if (p.stages > cap) p.stages = cap;
+  }
   if (p.stages < 2) return false;
   if (p.Rd * 16 >= (1 << 18) || p.Rx * 16 >= (1 << 18)) return false;
   // work items
