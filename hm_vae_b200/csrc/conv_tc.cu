@@ -128,12 +128,15 @@ __global__ void __launch_bounds__(128) conv_pack_kernel(ConvArgs a, const float*
     }
   }
   __syncthreads();
+  // Thread order follows the DESTINATION's innermost index (o for the fprop copy: 4 x 16 B = 64 contiguous bytes per (tap,
+  // chunk); c for the dgrad copy: ci x 16 contiguous bytes per tap), so the 16-byte stores of a warp coalesce; the shared-
+  // memory reads are strided instead (stride K = 15 words: conflict-free, stride ci*K: 4-way at worst).
   if (wp_f) {   // rows = o (4 of them), 16-byte groups over c
     const int qpb = kc_f / 4, nq = (a.ci + 3) / 4;
     for (int it = threadIdx.x; it < 4 * nq * a.K; it += blockDim.x) {
-      const int k = it % a.K;
-      const int q = (it / a.K) % nq;
-      const int i = it / (a.K * nq);
+      const int i = it & 3;
+      const int q = (it >> 2) % nq;
+      const int k = (it >> 2) / nq;
       const int o = o4 * 4 + i;
       if (o >= a.co) continue;
       float v[4];
@@ -147,9 +150,10 @@ __global__ void __launch_bounds__(128) conv_pack_kernel(ConvArgs a, const float*
     const int qpb = kc_d / 4;
     const int cb = o4 / qpb, h = o4 % qpb;
     for (int it = threadIdx.x; it < run; it += blockDim.x) {
-      const int k = it % a.K, c = it / a.K;
+      const int c = it % a.ci, k = it / a.ci;
+      const int x = c * a.K + k;
       wp_d[(long)e.base_d + ((long)((cb * a.K + k) * qpb + h) * e.cnt_d + e.slot_d) * npad_d + c] =
-          make_float4(rows[it], rows[run + it], rows[2 * run + it], rows[3 * run + it]);
+          make_float4(rows[x], rows[run + x], rows[2 * run + x], rows[3 * run + x]);
     }
   }
 }
@@ -697,8 +701,10 @@ static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mod
   p.tmem_cols = pow2;
   // split-K so that the grid fills one wave of SMs (fixed per-CTA cost dominates beyond that); >= 3 stages per CTA
   const int ctas = p.mtiles * L.groups;
-  int splits = num_sms() / ctas;
-  if (splits > L.longest / 3) splits = L.longest / 3;
+  // two CTAs fit an SM (2-stage rings): aim at 2 x SMs CTAs (measured: 148 / 296 / 444 / 592 -> 0.975 / 0.894 / 0.946 / 0.989 ms)
+  int splits = env_int("HMVAE_TC_TARGET_CTAS", 2 * num_sms()) / ctas;
+  const int min_len = env_int("HMVAE_TC_MIN_SPLIT_LEN", 3);
+  if (splits > L.longest / min_len) splits = L.longest / min_len;
   if (splits < 1) splits = 1;
   if (splits > 64) splits = 64;
   p.split_len = (L.longest + splits - 1) / splits;

@@ -489,7 +489,7 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
   {
     // split the (batch group, time window) stages over gridDim.y so that ~one wave of SMs is busy; >= 4 stages per CTA
     const int nst = p.mtiles * p.nwin;
-    int splits = p.nitems > 0 ? num_sms() / p.nitems : 1;
+    int splits = p.nitems > 0 ? env_int("HMVAE_WG_TARGET_CTAS", num_sms()) / p.nitems : 1;
     if (splits > nst / 4) splits = nst / 4;
     if (splits > 8) splits = 8;
     const long dense_bytes = (long)a.J * a.co * a.J * a.ci * a.K * 4;
