@@ -41,14 +41,14 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int num_sms();
 int env_int(const char* name, int dflt);   // tuning knobs (read once per call site is fine: geometry is memoised)
-bool pdl_enabled();   // HMVAE_PDL=1 (default off): programmatic dependent launch between consecutive kernels of a stream
+int pdl_level();      // HMVAE_PDL: 0 (default) off, 1 every hot-path kernel, 2 only kernels without a shared-memory footprint
 
 // Launch with the "programmatic stream serialization" attribute: the kernel may be scheduled while its predecessor in the
 // stream is still running; it runs its prologue (barrier init, TMEM allocation, constant tables) and then blocks in pdl_wait()
 // until the predecessor has completed and flushed.  A step here is ~100 dependent, mostly latency-bound launches, so hiding the
 // launch latency + prologue of each one matters.  RULE: every kernel launched through this helper calls pdl_wait() on every
 // control path before it touches global memory that another kernel writes or reads (completion must stay transitive).
-template <typename... KArgs, typename... Args>
+template <bool HEAVY = false, typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -59,7 +59,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const int lvl = pdl_level();
+  cfg.numAttrs = (lvl == 1 || (lvl == 2 && !HEAVY)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -14,15 +14,12 @@ int env_int(const char* name, int dflt) {
   return (e && e[0]) ? atoi(e) : dflt;
 }
 
-bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    // Measured on B200 (profiles/r01_summary_v3.md): back-to-back eager launches gain ~12 % device time, but inside the step's
-    // CUDA graph early-launched 200 KB-smem CTAs sit on SMs the other stream's kernels want (1.217 vs 1.205 ms) => opt-in.
-    const char* e = getenv("HMVAE_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;
-  }
-  return on != 0;
+int pdl_level() {
+  // Measured on B200 (profiles/r01_summary_v3.md): back-to-back eager launches gain ~12 % device time with level 1, but inside the
+  // step's CUDA graph early-launched 200 KB-smem CTAs sit on SMs the other stream's kernels want (1.217 vs 1.205 ms) => opt-in.
+  static int lvl = -1;
+  if (lvl < 0) lvl = env_int("HMVAE_PDL", 0);
+  return lvl;
 }
 
 int num_sms() {

@@ -772,7 +772,7 @@ int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, cons
   smem += 1024;
   HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.mtiles, (p.a.J + p.GJ - 1) / p.GJ, p.splits);
-  launch_pdl(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, p, reinterpret_cast<const unsigned char*>(workspace), wp, bias,
+  launch_pdl<true>(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, p, reinterpret_cast<const unsigned char*>(workspace), wp, bias,
              p.splits > 1 ? part : dst);
   int rc = check_launch(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
   if (rc || p.splits <= 1) return rc;

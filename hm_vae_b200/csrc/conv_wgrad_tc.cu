@@ -582,7 +582,7 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
   HMVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* part = reinterpret_cast<float*>(xw + wg_x_bytes(p));
   dim3 grid(p.nitems, p.psplits);
-  launch_pdl(conv_wgrad_tc_kernel, grid, dim3(WG_THREADS), smem, st, p, (const unsigned char*)dyw, (const unsigned char*)xw,
+  launch_pdl<true>(conv_wgrad_tc_kernel, grid, dim3(WG_THREADS), smem, st, p, (const unsigned char*)dyw, (const unsigned char*)xw,
              p.psplits > 1 ? part : dw, accumulate);
   int rc = check_launch("conv_wgrad_tc");
   if (rc || p.psplits <= 1) return rc;

@@ -114,8 +114,9 @@ class BucketedAllReduce:
             return
         self.comm_stream.wait_stream(torch.cuda.current_stream())
         from . import ops
-        if ops._overlap["side"] is not None and ops._overlap["pending"]:
-            self.comm_stream.wait_stream(ops._overlap["side"])       # weight gradients are produced on the side stream
+        if ops._overlap["pending"]:
+            for s in ops._overlap.get("used", ()) or ():             # weight gradients are produced on the side streams
+                self.comm_stream.wait_stream(s)
         with torch.cuda.stream(self.comm_stream):
             with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
                 for g in grads:
