@@ -60,7 +60,7 @@ DP_MAX_WORLD, DP_MAX_RANGES = 8, 64
 
 class DpPeers(Structure):
     _fields_ = [("world", c_int), ("rank", c_int), ("grad", c_void_p * DP_MAX_WORLD), ("param", c_void_p * DP_MAX_WORLD),
-                ("flags", c_void_p * DP_MAX_WORLD)]
+                ("flags", c_void_p * DP_MAX_WORLD), ("mc_grad", c_void_p), ("mc_param", c_void_p)]
 
 
 P = c_void_p

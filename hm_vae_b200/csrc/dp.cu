@@ -33,7 +33,22 @@ struct DpArgs {
   unsigned int* flags[HMVAE_DP_MAX_WORLD];      // [2 * world] per rank: entry flags, exit flags (indexed by the SIGNALLING rank)
   long beg[HMVAE_DP_MAX_RANGES], end[HMVAE_DP_MAX_RANGES];   // owned element ranges (multiples of 4, 16-byte aligned)
   int nranges;
+  const float* mc_grad;     // NVSwitch multicast mappings of the two arenas (NULL: unicast peer loads / stores)
+  float* mc_param;
 };
+
+// NVLS: one load returns the sum over all ranks' copies (reduced inside the switch), one store lands in every rank's copy
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -59,6 +74,7 @@ __device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int
   return true;
 }
 
+template <bool TWO>      // TWO: two float4 per thread and iteration (multi-rank: more peer loads in flight; costs registers)
 __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restrict__ m, float* __restrict__ v,
                                                       const float* __restrict__ dyn2, float beta1, float beta2, float eps,
                                                       float wd, float gscale, unsigned int* __restrict__ state) {
@@ -90,18 +106,90 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restric
   };
   for (int r = 0; r < A.nranges; ++r) {
     const long b4 = A.beg[r] >> 2, e4 = A.end[r] >> 2;
-    for (long i = b4 + tid; i < e4; i += nthreads) {
-      float4 G = __ldcg(reinterpret_cast<const float4*>(A.grad[0]) + i);
-      for (int q = 1; q < W; ++q) {
-        const float4 g2 = __ldcg(reinterpret_cast<const float4*>(A.grad[q]) + i);
-        G.x += g2.x; G.y += g2.y; G.z += g2.z; G.w += g2.w;
+    if (A.mc_grad != nullptr) {
+      // NVSwitch path: the reduce-scatter is one multimem.ld_reduce per element, the all-gather one multimem.st: every rank
+      // moves N/W elements each way instead of N(W-1)/W.
+      for (long i = b4 + tid; i < e4; i += 2 * nthreads) {           // two in-switch reductions in flight per thread
+        const long i2 = i + nthreads;
+        const bool two = i2 < e4;
+        const float4 G = multimem_ld_reduce_add(A.mc_grad + 4 * i);
+        float4 G2 = G;
+        if (two) G2 = multimem_ld_reduce_add(A.mc_grad + 4 * i2);
+        float4 P = reinterpret_cast<const float4*>(A.param[R])[i];
+        float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+        float4 P2 = P, M2 = M, V2 = V;
+        if (two) {
+          P2 = reinterpret_cast<const float4*>(A.param[R])[i2];
+          M2 = reinterpret_cast<float4*>(m)[i2];
+          V2 = reinterpret_cast<float4*>(v)[i2];
+        }
+        upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+        reinterpret_cast<float4*>(m)[i] = M;
+        reinterpret_cast<float4*>(v)[i] = V;
+        multimem_st(A.mc_param + 4 * i, P);
+        if (two) {
+          upd(P2.x, G2.x, M2.x, V2.x); upd(P2.y, G2.y, M2.y, V2.y); upd(P2.z, G2.z, M2.z, V2.z); upd(P2.w, G2.w, M2.w, V2.w);
+          reinterpret_cast<float4*>(m)[i2] = M2;
+          reinterpret_cast<float4*>(v)[i2] = V2;
+          multimem_st(A.mc_param + 4 * i2, P2);
+        }
+      }
+      continue;
+    }
+    if constexpr (!TWO) {
+      for (long i = b4 + tid; i < e4; i += nthreads) {
+        float4 G = __ldcg(reinterpret_cast<const float4*>(A.grad[0]) + i);
+        for (int q = 1; q < W; ++q) {
+          const float4 g2 = __ldcg(reinterpret_cast<const float4*>(A.grad[q]) + i);
+          G.x += g2.x; G.y += g2.y; G.z += g2.z; G.w += g2.w;
+        }
+        float4 P = reinterpret_cast<const float4*>(A.param[R])[i];
+        float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+        upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+        reinterpret_cast<float4*>(m)[i] = M;
+        reinterpret_cast<float4*>(v)[i] = V;
+        for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(A.param[q])[i] = P;
+      }
+      continue;
+    }
+    // two float4 per thread and iteration: 2 * W peer loads in flight before the first add (NVLink latency ~2-3 us)
+    for (long i = b4 + tid; i < e4; i += (TWO ? 2 : 1) * nthreads) {
+      const long i2 = i + nthreads;
+      const bool two = TWO && i2 < e4;
+      float4 Ga[HMVAE_DP_MAX_WORLD], Gb[HMVAE_DP_MAX_WORLD];
+#pragma unroll
+      for (int q = 0; q < HMVAE_DP_MAX_WORLD; ++q) {
+        if (q < W) {
+          Ga[q] = __ldcg(reinterpret_cast<const float4*>(A.grad[q]) + i);
+          if (two) Gb[q] = __ldcg(reinterpret_cast<const float4*>(A.grad[q]) + i2);
+        }
       }
       float4 P = reinterpret_cast<const float4*>(A.param[R])[i];
       float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+      float4 P2 = P, M2 = M, V2 = V;
+      if (two) {
+        P2 = reinterpret_cast<const float4*>(A.param[R])[i2];
+        M2 = reinterpret_cast<float4*>(m)[i2];
+        V2 = reinterpret_cast<float4*>(v)[i2];
+      }
+      float4 G = Ga[0], G2 = Gb[0];
+#pragma unroll
+      for (int q = 1; q < HMVAE_DP_MAX_WORLD; ++q) {
+        if (q < W) {                               // fixed order 0..W-1: deterministic
+          G.x += Ga[q].x; G.y += Ga[q].y; G.z += Ga[q].z; G.w += Ga[q].w;
+          if (two) { G2.x += Gb[q].x; G2.y += Gb[q].y; G2.z += Gb[q].z; G2.w += Gb[q].w; }
+        }
+      }
       upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
       reinterpret_cast<float4*>(m)[i] = M;
       reinterpret_cast<float4*>(v)[i] = V;
       for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(A.param[q])[i] = P;
+      if (two) {
+        upd(P2.x, G2.x, M2.x, V2.x); upd(P2.y, G2.y, M2.y, V2.y); upd(P2.z, G2.z, M2.z, V2.z); upd(P2.w, G2.w, M2.w, V2.w);
+        reinterpret_cast<float4*>(m)[i2] = M2;
+        reinterpret_cast<float4*>(v)[i2] = V2;
+        for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(A.param[q])[i2] = P2;
+      }
     }
   }
   __syncthreads();
@@ -146,6 +234,10 @@ extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* 
     if (on && (!aligned16(A.grad[q]) || !aligned16(A.param[q]))) return fail_arg("dp_adam_step: arenas must be 16-byte aligned");
   }
   if (!aligned16(m) || !aligned16(v)) return fail_arg("dp_adam_step: m / v must be 16-byte aligned");
+  A.mc_grad = peers->world > 1 ? peers->mc_grad : nullptr;
+  A.mc_param = peers->world > 1 ? peers->mc_param : nullptr;
+  if ((A.mc_grad == nullptr) != (A.mc_param == nullptr)) return fail_arg("dp_adam_step: both or neither multicast pointer");
+  if (A.mc_grad && (!aligned16(A.mc_grad) || !aligned16(A.mc_param))) return fail_arg("dp_adam_step: multicast pointers must be 16-byte aligned");
   long total = 0;
   A.nranges = nranges;
   for (int r = 0; r < nranges; ++r) {
@@ -159,7 +251,10 @@ extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* 
   const long cap = (long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  launch_pdl(dp_adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state);
+  if (A.world > 1 && A.mc_grad == nullptr)
+    launch_pdl(dp_adam_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state);
+  else
+    launch_pdl(dp_adam_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state);
   return check_launch("dp_adam_step");
 }
 

@@ -11,6 +11,7 @@ included, is one CUDA graph.
 The pure-Python helpers (``arena_layout``, ``merge_ranges``, ``owned_ranges``) are covered by the CPU tests (gloo, world 2).
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -76,6 +77,7 @@ class PeerArenas:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.numel, self.device, self.group = numel, device, group
         self.backend = None
+        self.mc_grad = self.mc_param = 0
         self._keep = []
         if self.world == 1:
             self.grad = torch.zeros(numel, device=device, dtype=torch.float32)
@@ -112,6 +114,17 @@ class PeerArenas:
         self.grad_ptrs, self.param_ptrs, self.flag_ptrs = [list(h.buffer_ptrs) for h in hdls]
         self._keep = hdls
         self.backend = "symmetric_memory"
+        # NVSwitch multicast (NVLS) mappings, when the fabric offers them
+        try:
+            mg, mp_ = int(hdls[0].multicast_ptr), int(hdls[1].multicast_ptr)
+        except Exception:       # noqa: BLE001
+            mg = mp_ = 0
+        # measured (B200, NVSwitch): ms/step unicast vs multicast = 0.955 / 1.007 (2 GPUs), 1.014 / 0.979 (4), 1.080 / 1.020 (8)
+        want = os.environ.get("HMVAE_DP_MULTICAST", "auto")
+        use = (self.world >= 3) if want == "auto" else (want != "0")
+        if mg and mp_ and use:
+            self.mc_grad, self.mc_param = mg, mp_
+            self.backend = "symmetric_memory+nvls_multicast"
 
     def _init_ipc(self):
         lib = _lib.lib
@@ -183,6 +196,8 @@ class FusedDataParallelAdam:
             peers.grad[q] = self.arenas.grad_ptrs[q]
             peers.param[q] = self.arenas.param_ptrs[q]
             peers.flags[q] = self.arenas.flag_ptrs[q]
+        peers.mc_grad = self.arenas.mc_grad or None
+        peers.mc_param = self.arenas.mc_param or None
         self._peers = peers
         self._range_cache = {}
         torch.cuda.synchronize()

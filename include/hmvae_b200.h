@@ -221,6 +221,8 @@ typedef struct {
   const float* grad[HMVAE_DP_MAX_WORLD];
   float* param[HMVAE_DP_MAX_WORLD];
   unsigned int* flags[HMVAE_DP_MAX_WORLD];
+  const float* mc_grad;   /* optional NVSwitch multicast (NVLS) mappings of the gradient / parameter arenas: when both are set the */
+  float* mc_param;        /* kernel uses multimem.ld_reduce / multimem.st (in-switch reduction and replication); else NULL          */
 } hmvae_dp_peers;
 int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges, const float* dyn2,
                        float beta1, float beta2, float eps, float weight_decay, float grad_scale, unsigned int* state,
