@@ -166,9 +166,7 @@ class Trainer(nn.Module):
         self.gen_opt.advance(lr=self.lr_at(iterations))
         if key in self._graphs:
             graph, static_in, static_out = self._graphs[key]
-            for dst, src in zip(static_in, data):
-                if dst is not None:
-                    dst.copy_(src, non_blocking=True)
+            self._load_inputs(static_in, data)
             graph.replay()
             out = static_out
             if self._sync.world > 1 and not self._sync.fused:
@@ -178,6 +176,40 @@ class Trainer(nn.Module):
         else:
             out = self._device_step(data, hp, iterations)
         return self._record(out, False)
+
+    def _load_inputs(self, static_in, data):
+        """Moves this step's inputs into the graph's static buffers.  Host (pinned) inputs go through a copy stream into a
+        double-buffered staging area first, so the H2D transfer of step i+1 runs while the graph of step i is still executing
+        (the static buffers themselves are read until the loss kernel at the end of the forward pass)."""
+        host = [i for i, (dst, src) in enumerate(zip(static_in, data)) if dst is not None and torch.is_tensor(src) and not src.is_cuda]
+        if not host:
+            for dst, src in zip(static_in, data):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            return
+        if getattr(self, "_stage", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = [[torch.empty_like(t) if t is not None else None for t in static_in] for _ in range(2)]
+            self._stage_ev = [None, None]
+            self._stage_free = [None, None]
+            self._stage_k = 0
+        k = self._stage_k = self._stage_k ^ 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_free[k] is not None:
+                self._copy_stream.wait_event(self._stage_free[k])        # the step that used this slot has consumed it
+            for i in host:
+                self._stage[k][i].copy_(data[i], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        main.wait_event(ev)
+        for i, (dst, src) in enumerate(zip(static_in, data)):
+            if dst is None:
+                continue
+            dst.copy_(self._stage[k][i] if i in host else src, non_blocking=True)
+        free = torch.cuda.Event()
+        free.record()
+        self._stage_free[k] = free
 
     # ------------------------------------------------------------------ CUDA graph of the whole step
     def _graph_key(self, hp, iterations, data):
