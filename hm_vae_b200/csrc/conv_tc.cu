@@ -522,9 +522,9 @@ static void tc_build_layer(const hmvae_conv_plan* plan, int mode, TcLayer* L) {
   L->ck_pad = rup(L->ck, 8);
   if (a.J > 64 || L->n_pad > 256) return;
   L->KC = tc_pick_kc(L->ck_pad, L->n_pad, a.K);
-  L->GJ = 64 / L->n_pad;
+  L->GJ = env_int("HMVAE_TC_GROUP_COLS", 64) / L->n_pad;      // output joints per CTA (accumulator columns / n_pad)
   if (L->GJ < 1) L->GJ = 1;
-  if (L->GJ > 4) L->GJ = 4;
+  if (L->GJ > env_int("HMVAE_TC_GROUP_MAX", 4)) L->GJ = env_int("HMVAE_TC_GROUP_MAX", 4);
   if (L->GJ > a.J) L->GJ = a.J;
   L->groups = (a.J + L->GJ - 1) / L->GJ;
   // N-side joint -> K-side joints (fprop: neighbour list; dgrad: transpose, ascending)
