@@ -217,7 +217,7 @@ using namespace hmvae;
 
 extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges,
                                   const float* dyn2, float beta1, float beta2, float eps, float weight_decay,
-                                  float grad_scale, unsigned int* state, void* stream) {
+                                  float grad_scale, unsigned int* state, int max_ctas, void* stream) {
   if (!peers || !m || !v || !dyn2 || !state || (nranges > 0 && !ranges)) return fail_arg("dp_adam_step: null pointer");
   if (peers->world < 1 || peers->world > HMVAE_DP_MAX_WORLD || peers->rank < 0 || peers->rank >= peers->world)
     return fail_arg("dp_adam_step: bad world / rank");
@@ -250,6 +250,7 @@ extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* 
   long blocks = (total / 4 + 255) / 256;
   const long cap = (long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
+  if (max_ctas > 0 && blocks > max_ctas) blocks = max_ctas;      // a call that runs under other kernels leaves them room
   if (blocks < 1) blocks = 1;
   if (A.world > 1 && A.mc_grad == nullptr)
     launch_pdl(dp_adam_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state);

@@ -226,11 +226,12 @@ class FusedDataParallelAdam:
         self._dyn_host[0] = lr / (1.0 - self.betas[0] ** self.step_count)
         self._dyn_host[1] = 1.0 / (1.0 - self.betas[1] ** self.step_count) ** 0.5
 
-    def _live_ranges(self):
-        """Live = parameters that received a gradient this step.  Gradients that autograd did not place in the arena (it
-        clones a gradient it cannot steal) are copied in."""
+    def _live_ranges(self, select):
+        """Live = parameters (with index in ``select``) that received a gradient this step.  Gradients that autograd did not
+        place in the arena (it clones a gradient it cannot steal) are copied in."""
         key, live = [], []
-        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+        for i in select:
+            p, off = self.params[i], self.offsets[i]
             if p.grad is None:
                 continue
             n = p.numel()
@@ -246,22 +247,58 @@ class FusedDataParallelAdam:
             flat = (ctypes.c_long * (2 * max(len(own), 1)))()
             for k, (b, e) in enumerate(own):
                 flat[2 * k], flat[2 * k + 1] = b, e
-            self._range_cache[key] = (flat, len(own))
+            self._range_cache[key] = (flat, len(own), key)
         return self._range_cache[key]
 
-    def step_dyn(self, grad_scale=None):
-        """Device side (capturable).  ``grad_scale`` defaults to 1/world (mean of the per-rank gradients)."""
+    def _launch(self, select, grad_scale, max_ctas=0):
         from . import ops
 
-        flat, n = self._live_ranges()
-        self._dyn_dev.copy_(self._dyn_host, non_blocking=True)
-        for p in self.params:
-            if p.grad is not None:
-                torch.autograd.graph.increment_version(p)
+        flat, n, live = self._live_ranges(select)
+        for i in live:
+            torch.autograd.graph.increment_version(self.params[i])
         scale = (1.0 / self.world) if grad_scale is None else grad_scale
         _lib.check(_lib.lib.hmvae_dp_adam_step(ctypes.byref(self._peers), _lib.ptr(self.m), _lib.ptr(self.v), flat, n,
                                                _lib.ptr(self._dyn_dev), self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                               scale, self.state.data_ptr(), ops.stream()), "dp_adam_step")
+                                               scale, self.state.data_ptr(), int(max_ctas), ops.stream()), "dp_adam_step")
+
+    def begin_step(self):
+        """Start of a device step (capturable): the step-dependent scalars go to the device; nothing has been stepped yet."""
+        self._dyn_dev.copy_(self._dyn_host, non_blocking=True)
+        self._stepped = set()
+        self._begun = True
+
+    def step_partial(self, param_ids, grad_scale=None):
+        """Steps ONLY the given parameters, now, on a side stream: called in the middle of the backward pass as soon as their
+        gradients are final (the decoder's, while the encoder's backward still runs), so that part of the collective + optimiser
+        work hides under the rest of backward.  Every rank must make the same sequence of calls."""
+        from . import ops
+
+        if not getattr(self, "_begun", False):
+            self.begin_step()
+        select = [i for i, p in enumerate(self.params) if id(p) in param_ids and i not in self._stepped]
+        if not select:
+            return
+        if getattr(self, "_opt_stream", None) is None:
+            self._opt_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._opt_stream.wait_stream(main)
+        for s in ops._overlap.get("used", ()) or ():           # weight gradients are produced on the side stream(s)
+            self._opt_stream.wait_stream(s)
+        with torch.cuda.stream(self._opt_stream):
+            self._launch(select, grad_scale, max_ctas=int(os.environ.get("HMVAE_DP_PARTIAL_CTAS", "296")))
+        self._stepped.update(select)
+        self._partial_pending = True
+
+    def step_dyn(self, grad_scale=None):
+        """Device side (capturable): everything not stepped by ``step_partial`` in this step.  ``grad_scale`` defaults to
+        1/world (mean of the per-rank gradients)."""
+        if not getattr(self, "_begun", False):
+            self.begin_step()
+        if getattr(self, "_partial_pending", False):
+            torch.cuda.current_stream().wait_stream(self._opt_stream)     # also orders the two kernels' epochs / flags
+            self._partial_pending = False
+        self._launch([i for i in range(len(self.params)) if i not in self._stepped], grad_scale)
+        self._begun = False
 
     def step(self, grad_scale=None, lr=None):
         self.advance(lr)

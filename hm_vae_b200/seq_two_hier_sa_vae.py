@@ -237,6 +237,7 @@ class TwoHierSAVAEModel(nn.Module):
         self.std_vals = torch.from_numpy(mean_std[1, :]).float()[None, :].to(dev)
         self._parents = parents
         self._const = {}
+        self.mid_backward = None      # optional callback: decoder gradients are final (set by Trainer for the split optimiser step)
 
     def get_hier_level(self, step):
         return 1 if step < self.iteration_interval else 4
@@ -300,6 +301,12 @@ class TwoHierSAVAEModel(nn.Module):
                 z = ops.latent_fused(dist, eps[zi], lat[zi], kl_w / (bs * k_edges[zi]), slot)
             z_list[zi] = z.view(bs, k_edges[zi], -1)
 
+        # Split backward (when a mid-backward callback is installed): the decoder runs on detached latents, so that its
+        # backward finishes -- and its optimiser / collective share can start -- before the encoder's backward begins.
+        split = self.mid_backward is not None and not validation_flag
+        z_enc = list(z_list)
+        if split:
+            z_list = [z.detach().requires_grad_(z.requires_grad) if z is not None else None for z in z_list]
         out = self.dec(z_list)                                      # bs X (24*6) X T
         fk_off = self.fk_layer.positions[0].contiguous()
         dx6 = ops.recon_fwdbwd(out.detach(), True, seq_rot_6d, seq_rot_mat, fk_off, self._parents, hp['rec_6d_w'],
@@ -319,6 +326,11 @@ class TwoHierSAVAEModel(nn.Module):
         if not validation_flag:
             with ops.wgrad_overlap():
                 out.backward(dx6)
+                if split:
+                    self.mid_backward()
+                    pairs = [(ze, zd.grad) for ze, zd in zip(z_enc, z_list) if ze is not None and ze.requires_grad and zd.grad is not None]
+                    if pairs:
+                        torch.autograd.backward([a for a, _ in pairs], [g for _, g in pairs])
 
         return l_total, l_kl, l_rec_6d, l_rec_rot_mat, l_rec_pose, zero, zero, zero, zero, l_kl_list
 

@@ -112,6 +112,16 @@ class Trainer(nn.Module):
                                                          prefer=os.environ.get("HMVAE_DP_PEER", "symm"))
                     self._sync = _NoCollective(world)
                     self.dp_mode = "fused_peer_memory(%s)" % self.gen_opt.arenas.backend
+                    # The decoder's share of the optimiser step starts as soon as the decoder's gradients are final and runs under
+                    # the encoder's backward.  Measured: 1 GPU 0.910 -> 0.890 ms per step; 2 GPUs 0.955 -> 1.006 (the early
+                    # kernel waits for its peers while sitting on SMs the encoder backward wants) => on by default only for 1 rank.
+                    dec = getattr(self.model, "dec", None)
+                    split = os.environ.get("HMVAE_DP_SPLIT", "auto")
+                    if dec is not None and (world == 1 if split == "auto" else split != "0"):
+                        enc_ids = {id(p) for p in self.model.enc.parameters()}
+                        dec_ids = {id(p) for p in dec.parameters()} - enc_ids
+                        self.model.mid_backward = lambda: self.gen_opt.step_partial(dec_ids, grad_scale=1.0 / world)
+                        self.dp_mode += "+split"
                     return
                 except ops._lib.HmvaeError as exc:
                     if self._dp_fused:
@@ -130,6 +140,8 @@ class Trainer(nn.Module):
     # ------------------------------------------------------------------ one step
     def _device_step(self, data, hp, iterations):
         self.gen_opt.zero_grad(set_to_none=True)
+        if self._sync.fused:
+            self.gen_opt.begin_step()
         self._sync.begin()
         out = self.model(data, hp, iterations)
         self._sync.finish()

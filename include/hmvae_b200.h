@@ -213,7 +213,9 @@ int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const f
  *   ranges : HOST array [nranges][2] of element ranges [begin, end) owned by THIS rank (multiples of 4); m / v: this rank's
  *            full-size moment arenas (only the owned ranges are touched).   dyn2: device float[2] as in hmvae_adam_step_dyn.
  *   state  : device uint32[4], zero-initialised once: {epoch, CTA counter, timeout flag, -}.
- * Every rank must call it the same number of times.  world == 1 degenerates to a plain fused Adam over the ranges. */
+ * max_ctas : 0 = size the grid for the whole GPU; > 0 caps it (a call issued in the middle of the backward pass, for the
+ *            parameters whose gradients are already final, should leave SMs to the kernels it overlaps with).
+ * Every rank must make the same sequence of calls.  world == 1 degenerates to a plain fused Adam over the ranges. */
 #define HMVAE_DP_MAX_WORLD 8
 #define HMVAE_DP_MAX_RANGES 64
 typedef struct {
@@ -226,7 +228,7 @@ typedef struct {
 } hmvae_dp_peers;
 int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges, const float* dyn2,
                        float beta1, float beta2, float eps, float weight_decay, float grad_scale, unsigned int* state,
-                       void* stream);
+                       int max_ctas, void* stream);
 /* Peer-memory plumbing over CUDA IPC (used when torch's symmetric memory is unavailable): zero-filled device allocation, its
  * 64-byte handle, and mapping / unmapping of another process's handle. */
 int hmvae_ipc_alloc(long bytes, void** ptr);
