@@ -202,6 +202,19 @@ int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, f
 int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const float* dyn2, float beta1, float beta2,
                         float eps, float weight_decay, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ batch assembly (utils_motion_vae.py, the step before the path)
+ *
+ * rand_rotation_matrix (:17-57): randnums [n,3] float64 in [0,1] -> rot [n,9] float32 (row-major), computed in float64. */
+int hmvae_rand_rotation(const double* randnums, double deflection, float* rot, long n, void* stream);
+/* MotionSeqData.__getitem__ (:140-187) for a batch of already cropped windows raw [batch, t, 579]: the seven training tensors
+ * rot6d [B,T,144], rotmat [B,T,216], rot_pos [B,T,72] (raw), joint_pos / linear_v / angular_v [B,T,72] and root_v [B,T,3]
+ * (standardised with mean / std, float64 [579], zero stds already replaced by 1); any output may be NULL.  root_rot [batch, 9]
+ * (one rotation per sequence, hmvae_rand_rotation) switches on the random-root-rotation augmentation (:167-185): root matrix
+ * and root velocity are rotated, the 6D representation is re-derived from the matrices; NULL = no augmentation. */
+int hmvae_batch_assemble(const float* raw, const float* root_rot, const double* mean, const double* stdv, int batch, int t,
+                         float* rot6d, float* rotmat, float* rot_pos, float* joint_pos, float* linear_v, float* angular_v,
+                         float* root_v, void* stream);
+
 /* ------------------------------------------------------------------ data parallelism (train_motion_vae.py:49-53)
  *
  * The optimiser step fused with its collective over NVLink peer memory: every rank owns a share of the parameter elements;

@@ -11,6 +11,8 @@ activation mask held fixed; (2) the whole backward chain is checked strictly (2e
 shares every line of host logic with the tensor-core path; (3) tensor-core whole-model gradients get a loose 0.15
 relative-L2 sanity bound plus 2e-3 on the losses.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -507,3 +509,50 @@ def test_graph_step_with_pinned_host_inputs_matches_device_inputs(smpl):
         ops.unregister_grad_buffers()
     np.testing.assert_allclose(runs[0], runs[1], rtol=1e-6)
     assert len(set(round(v, 5) for v in runs[0][:4])) == 4      # different batches really gave different losses
+
+
+# ------------------------------------------------------------------------------------------------ batch assembly
+def test_rand_rotation_kernel_vs_reference_golden():
+    from hm_vae_b200 import utils_motion_vae as U
+
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "batch.npz")))
+    np.testing.assert_allclose(U.rand_rotation_matrices(g["rr_randnums"], 1.0).cpu().numpy(), g["rr_full"].astype(np.float32), atol=1e-7)
+    np.testing.assert_allclose(U.rand_rotation_matrices(g["rr_randnums"], 0.25).cpu().numpy(), g["rr_small"].astype(np.float32), atol=1e-7)
+    np.testing.assert_allclose(U.rand_rotation_matrix(1.0, g["rr_randnums"][0]), g["rr_full"][0], atol=1e-15)
+
+
+@pytest.mark.parametrize("tag", ["plain", "rot", "rot64", "fps_rot"])
+def test_batch_assemble_vs_reference_golden(smpl, tag):
+    """hmvae_batch_assemble against the outputs of the REAL MotionSeqData.__getitem__ on the same window / random numbers."""
+    from hm_vae_b200 import utils_motion_vae as U
+
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "batch.npz")))
+    idx, T, freq, t0, rot = [int(v) for v in g[f"{tag}_meta"]]
+    window = g[f"seq{idx}"][0::freq][t0:t0 + T]
+    asm = U.DeviceBatchAssembler(smpl["mean_std"], random_root_rot_flag=bool(rot), device=DEV)
+    raw = torch.from_numpy(np.stack([window, window[::-1].copy()]))            # batch of 2: the window and its time reversal
+    rn = np.stack([g[f"{tag}_randnums"], g[f"{tag}_randnums"]]) if rot else None
+    out = asm(raw, randnums=rn)
+    names = ["rot6d", "rotmat", "rot_pos", "joint_pos", "linear_v", "angular_v", "root_v"]
+    for n, v in zip(names, out):
+        ref = g[f"{tag}_{n}"]
+        got = v.cpu().numpy()
+        assert got.shape == (2,) + ref.shape
+        if n in ("rot_pos", "joint_pos", "linear_v", "angular_v") or not rot:
+            np.testing.assert_array_equal(got[0], ref, err_msg=n)               # copies / float64 standardisation: bit-exact
+            np.testing.assert_array_equal(got[1], ref[::-1], err_msg=n)
+        else:
+            np.testing.assert_allclose(got[0], ref, rtol=2e-6, atol=2e-6, err_msg=n)
+            np.testing.assert_allclose(got[1], ref[::-1], rtol=2e-6, atol=2e-6, err_msg=n)
+    # and against the oracle restatement on a larger random batch
+    from oracle import batch_ref as BR
+    rng = np.random.RandomState(3)
+    big = rng.randn(5, 33, 579).astype(np.float32)
+    rns = rng.uniform(size=(5, 3))
+    ms = smpl["mean_std"].copy()
+    ms[1, ms[1] == 0] = 1.0
+    outs = U.DeviceBatchAssembler(smpl["mean_std"], random_root_rot_flag=True, device=DEV)(big, randnums=rns)
+    for b in range(5):
+        want = BR.assemble(big[b], ms, BR.rand_rotation_matrix(1.0, rns[b]))
+        for n, v, w in zip(names, outs, want):
+            np.testing.assert_allclose(v[b].cpu().numpy(), w, rtol=3e-6, atol=3e-6, err_msg=n)
