@@ -44,6 +44,7 @@ struct TcArgs {
   int Bt, Tt;          // sequences per tile, rows-per-sequence (M = Tt*Bt <= 128)
   int rows_alloc;      // rows per 16-byte chunk column of an activation tile
   int Tp2;             // fprop stride 2: rows per phase / Bt
+  int ntt, U;          // dgrad time tiling (T + 2p > 128): tiles per sequence (1 = none), result time steps owned by a tile
   int GJ, nbmax, stages;
   int B, T, T_out, mtiles;
   int a_bytes, stage_bytes;
@@ -87,6 +88,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// dgrad time tiling: a tile is a window of 128 consecutive rows (padded input positions) of ONE sequence.  Tile tt owns the
+// result steps u in [tt*U, (tt+1)*U); its window starts at 0 for the first tile, ends at Tq for the last one (so that the rows the
+// reflect-padding fold needs are inside), and is centred on the owned rows otherwise.
+__host__ __device__ __forceinline__ int tc_tile_t0(int tt, int ntt, int U, int pad, int Tq) {
+  if (ntt <= 1 || tt == 0) return 0;
+  if (tt == ntt - 1) return Tq - 128;
+  int t0 = tt * U + pad - (128 - U) / 2;
+  if (t0 < 0) t0 = 0;
+  if (t0 > Tq - 128) t0 = Tq - 128;
+  return t0;
 }
 
 __device__ __forceinline__ long tc_out_index(const ConvArgs& a, long b, int j, int o, int t, int T_out) {
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(TcArgs p, const float
   pdl_wait();
   const ConvArgs& a = p.a;
   const int Tq = p.T + 2 * a.p;
-  const int tfill = (p.mode == 0) ? Tq : (Tq + a.K - 1);
+  const int tfill = (p.mode == 0) ? Tq : ((p.ntt > 1 ? 128 : Tq) + a.K - 1);
   const int nq = p.ck_pad / 4;             // 16-byte chunks per K-side joint
   const int qpb = p.KC / 4;                // chunks per stage block
   const long per_mt = (long)a.J * nq * p.Bt * tfill;
@@ -178,7 +191,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(TcArgs p, const float
     const int q = (int)(rest % nq); rest /= nq;
     const int n = (int)(rest % a.J);
     const int mt = (int)(rest / a.J);
-    const long bb = (long)mt * p.Bt + b;
+    const long bb = (p.ntt > 1) ? mt / p.ntt : (long)mt * p.Bt + b;
     const int c0 = q * 4;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     int row;
@@ -191,7 +204,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(TcArgs p, const float
       }
     } else {
       row = r * p.Bt + b;
-      const int zz = r - (a.K - 1);
+      const int zz = r + tc_tile_t0(p.ntt > 1 ? mt % p.ntt : 0, p.ntt, p.U, a.p, Tq) - (a.K - 1);
       if (bb < p.B && zz >= 0 && (zz % a.s) == 0 && zz / a.s < p.T_out) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -238,7 +251,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   const int mt = blockIdx.x;
   const int j0 = blockIdx.y * p.GJ;
   const int gj = (a.J - j0 < p.GJ) ? a.J - j0 : p.GJ;
-  const int b0 = mt * p.Bt;
+  // first sequence of the tile; with dgrad time tiling (Bt == 1) a sequence spans ntt tiles and a tile only owns result steps
+  // [u_lo, u_lo + ucnt) (fprop / untiled dgrad: all of them)
+  const int b0 = (p.ntt > 1) ? mt / p.ntt : mt * p.Bt;
+  const int tt = (p.ntt > 1) ? mt % p.ntt : 0;
+  const int t0 = tc_tile_t0(tt, p.ntt, p.U, a.p, p.T + 2 * a.p);
+  const int Tres = (p.mode == 0) ? p.T_out : p.T;
+  const int u_lo = (p.ntt > 1) ? tt * p.U : 0;
+  const int ucnt = (p.ntt > 1) ? ((Tres - u_lo < p.U) ? Tres - u_lo : p.U) : Tres;
   const int ncb = p.ck_pad / p.KC;
   const int qpb = p.KC / 4;
 
@@ -399,10 +419,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
       // partial sums: plain [split][B][J*n_real][Tr] layout (Tr = T_out for fprop, T for dgrad), finished by conv_tc_finish_kernel
       const int Tr = (p.mode == 0) ? p.T_out : p.T;
       float* part = dst + (size_t)blockIdx.z * p.B * a.J * p.n_real * Tr;
-      const int total = nch * p.Bt * Tr;
+      const int total = nch * p.Bt * ucnt;
       for (int e = pt; e < total; e += 128) {
-        const int u = e % Tr;
-        const int r = e / Tr;
+        const int u = u_lo + e % ucnt;
+        const int r = e / ucnt;
         const int b = r % p.Bt, ch = r / p.Bt;
         if (b0 + b < p.B) {
           float v;
@@ -410,10 +430,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
             v = outs[(size_t)ch * 128 + u * p.Bt + b];
           } else {
             const float* row = outs + (size_t)ch * 128 + b;
-            v = row[(u + a.p) * p.Bt];
+            v = row[(u + a.p - t0) * p.Bt];
             if (a.pad_mode == 1) {
-              if (u >= 1 && u <= a.p) v += row[(a.p - u) * p.Bt];
-              if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += row[(a.p + 2 * (p.T - 1) - u) * p.Bt];
+              if (u >= 1 && u <= a.p) v += row[(a.p - u - t0) * p.Bt];
+              if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += row[(a.p + 2 * (p.T - 1) - u - t0) * p.Bt];
             }
           }
           part[((size_t)(b0 + b) * a.J * p.n_real + (size_t)j0 * p.n_real + ch) * Tr + u] = v;
@@ -433,19 +453,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
         }
       }
     } else {
-      const int total = nch * p.Bt * p.T;
+      const int total = nch * p.Bt * ucnt;
       const int Cin = a.J * a.ci;
       for (int e = pt; e < total; e += 128) {
-        const int u = e % p.T;
-        const int r = e / p.T;
+        const int u = u_lo + e % ucnt;
+        const int r = e / ucnt;
         const int b = r % p.Bt, ch = r / p.Bt;
         if (b0 + b < p.B) {
           const int jl = ch / p.n_real, c = ch % p.n_real;
           const float* row = outs + (size_t)ch * 128 + b;
-          float v = row[(u + a.p) * p.Bt];
+          float v = row[(u + a.p - t0) * p.Bt];
           if (a.pad_mode == 1) {
-            if (u >= 1 && u <= a.p) v += row[(a.p - u) * p.Bt];
-            if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += row[(a.p + 2 * (p.T - 1) - u) * p.Bt];
+            if (u >= 1 && u <= a.p) v += row[(a.p - u - t0) * p.Bt];
+            if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += row[(a.p + 2 * (p.T - 1) - u - t0) * p.Bt];
           }
           dst[((long)(b0 + b) * Cin + (j0 + jl) * a.ci + c) * p.T + u] = v;
         }
@@ -661,9 +681,25 @@ static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mod
   p.Tt = (mode == 0) ? p.T_out : Tq;
   p.n_real = L.n_real; p.n_pad = L.n_pad; p.ck = L.ck; p.ck_pad = L.ck_pad; p.KC = L.KC; p.GJ = L.GJ; p.nbmax = L.nbmax;
   p.wtab = L.dev_work;
-  if (p.Tt > 128 || p.Tt < 1) return false;
-  p.Bt = 128 / p.Tt;
-  if (p.Bt > B) p.Bt = B;
+  p.ntt = 1;
+  p.U = (mode == 0) ? p.T_out : T;
+  if (p.Tt < 1) return false;
+  if (p.Tt > 128) {
+    // dgrad of long sequences (trajectory model: T = 128, K = 31 => 158 padded rows): tile over time, one sequence per tile
+    if (mode == 0) return false;
+    int n = 2;
+    for (; n <= 64; ++n) {
+      const int U = (T + n - 1) / n;
+      if (U + 2 * a.p <= 128 && U >= a.p + 1) break;
+    }
+    if (n > 64 || 2 * a.p + 1 > 128) return false;
+    p.ntt = n;
+    p.U = (T + n - 1) / n;
+    p.Bt = 1;
+  } else {
+    p.Bt = 128 / p.Tt;
+    if (p.Bt > B) p.Bt = B;
+  }
   p.Tp2 = (Tq + 1) / 2;
   if (mode == 0) {
     if (a.s == 1) p.rows_alloc = (a.K - 1) * p.Bt + 128;
@@ -675,12 +711,12 @@ static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mod
     if (fill > p.rows_alloc) p.rows_alloc = fill;
   } else {
     p.rows_alloc = (a.K - 1) * p.Bt + 128;
-    const int fill = (Tq + a.K - 1) * p.Bt;
+    const int fill = ((p.ntt > 1 ? 128 : Tq) + a.K - 1) * p.Bt;
     if (fill > p.rows_alloc) p.rows_alloc = fill;
   }
   p.rows_alloc = rup(p.rows_alloc, 8);
   if (p.rows_alloc * 16 >= (1 << 18)) return false;
-  p.mtiles = (B + p.Bt - 1) / p.Bt;
+  p.mtiles = (p.ntt > 1) ? B * p.ntt : (B + p.Bt - 1) / p.Bt;
   p.a_bytes = (p.KC / 4) * p.rows_alloc * 16;
   p.stage_bytes = rup(p.a_bytes + L.nbmax * a.K * (p.KC / 4) * p.n_pad * 16, 128);
   const int budget = env_int("HMVAE_TC_SMEM_KB", 208) * 1024;     // dynamic shared memory per CTA (stage ring)
