@@ -53,3 +53,23 @@ def test_change_fps_factor_rule():
     seq = iter([12, 10, 8, 6, 5, 4, 3, 2, 1, 1])
     assert BR.change_fps_factor(40, 8, lambda: next(seq)) == 5           # 12, 10, 8, 6 leave < 8 frames; 5 leaves 8
     assert BR.change_fps_factor(5, 8, lambda: 2) == 1                    # never enough: the original data
+
+
+@pytest.mark.parametrize("tag,seed,fps", [("plain", 11, False), ("rot", 12, False), ("rot64", 13, False), ("fps_rot", 14, True)])
+def test_host_mirror_draws_the_same_window_as_the_reference(gold, tag, seed, fps):
+    """hm_vae_b200.utils_motion_vae keeps the reference's host-side index logic and RNG consumption order: with the generators
+    seeded like oracle/make_golden_batch.py seeded them, it crops the window and draws the three numbers the reference used."""
+    import random
+
+    from hm_vae_b200 import utils_motion_vae as U
+
+    idx, T, freq, t0, rot = [int(v) for v in gold[f"{tag}_meta"]]
+    random.seed(seed)
+    np.random.seed(seed)
+    window = U.crop_window(gold[f"seq{idx}"], T, fps_aug_flag=fps)
+    np.testing.assert_array_equal(window, gold[f"seq{idx}"][0::freq][t0:t0 + T])
+    if rot:
+        rnd = np.random.uniform(size=(3,))
+        np.testing.assert_array_equal(rnd, gold[f"{tag}_randnums"])
+        np.testing.assert_allclose(U.rand_rotation_matrix(1.0, rnd), BR.rand_rotation_matrix(1.0, rnd), atol=1e-15)
+    assert U.crop_window(gold["seq0"][:5], 8) is None          # too short: the reference draws another sequence

@@ -17,12 +17,15 @@ from hm_vae_b200.trainer_motion_vae import Trainer  # noqa: E402
 rank, world, local = ddp.init_from_env("nccl")
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-hp = yaml.safe_load(open(os.path.join(os.path.dirname(__file__), "..", "configs", "len64_no_aug_hm_vae.yaml")))
+cfg_name = sys.argv[1] if len(sys.argv) > 1 else "len64_no_aug_hm_vae.yaml"      # or trajectory_model.yaml (BASELINE config 5)
+hp = yaml.safe_load(open(os.path.join(os.path.dirname(__file__), "..", "configs", cfg_name)))
 bs, T = 8, hp["train_seq_len"]
 g = torch.Generator().manual_seed(100 + rank)
 x6 = torch.randn(bs, T, 24, 6, generator=g).to(dev)
 rot = ops.rot6d_to_rotmat(x6)
 data = (torch.stack((rot[..., 0], rot[..., 1]), dim=-2).reshape(bs, T, -1).contiguous(), rot.reshape(bs, T, -1).contiguous())
+if hp["model_name"] == "TrajectoryModel":
+    data = (data[0], data[1], None, torch.randn(bs, T, 72, generator=g).to(dev), None, None, torch.randn(bs, T, 3, generator=g).to(dev))
 out = {}
 for fused in (False, True):
     torch.manual_seed(0)
