@@ -383,18 +383,18 @@ def run_b200(args, hp):
     e1.record()
     barrier()
     ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
-    # the clock sampler (100 ms period) needs >= ~1 s under load: keep stepping (untimed) if the two timed regions were shorter
-    t_load = time.perf_counter()
-    while (ms + ms_e2e) * args.steps * 1e-3 + (time.perf_counter() - t_load) < 1.2:
-        for _ in range(20):
-            trainer.gen_update(data, hp, iters0)
-        torch.cuda.synchronize()
-    clocks = sampler.stop()
-
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    # The clock sampler (100 ms period) needs >= ~1 s under load: keep stepping (untimed) if the two timed regions were shorter.
+    # The NUMBER of extra steps is derived from the all-reduced times, so every rank runs the same count (each step contains the
+    # cross-rank optimiser kernel: ranks must make identical call sequences).
+    n_extra = int(max(0.0, 1.2 - (ms + ms_e2e) * args.steps * 1e-3) / (ms * 1e-3)) + 1
+    for _ in range(n_extra):
+        trainer.gen_update(data, hp, iters0)
+    barrier()
+    clocks = sampler.stop()
 
     # ---- per-kernel attribution (eager, CUDA events around each C-ABI call, after the timed region).  The steps contain the
     #      gradient all-reduce, so EVERY rank runs them; only rank 0 reports.  Pass 1: one event pair per call (includes host
@@ -447,15 +447,17 @@ def run_b200(args, hp):
                     "kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])},
                     "kernel_ms_total_per_step_eager": total_kernel_ms,
                     "conv_us_per_layer": kt8.per_layer(prof_steps)}
-        fk = fk_sweep(dev, pk) if args.fk_sweep else None
+        # the single-GPU legs (FK sweep, B=512 inference, CPU baseline) are reported at N = 1 only: at N > 1 the other ranks
+        # would just wait for rank 0
+        fk = fk_sweep(dev, pk) if (args.fk_sweep and world == 1) else None
         big = None
-        if args.large_batch:
+        if args.large_batch and world == 1:
             try:
                 big = inference_leg(model, hp, dev, pk)
             except Exception as exc:        # reported, never fatal for the headline line
                 big = {"error": "%s: %s" % (type(exc).__name__, exc)}
         cpu = None
-        if args.cpu_baseline:
+        if args.cpu_baseline and world == 1:
             sec, threads = cpu_reference_step_time(hp, bs, 60, 3)
             cpu = {"value": bs / sec, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "60 timed steps of B=%d after 3 warm-up (oracle/hmvae_ref.py, torch CPU fp32, fwd+bwd+Adam)" % bs}
@@ -466,6 +468,7 @@ def run_b200(args, hp):
                                        "T=64, 24-joint SMPL, random-init weights" % bs,
                            "global_batch": world * bs, "parallelism": "dp%d" % world, "cuda_graph": bool(args.graph),
                            "conv_impl": args.conv_impl, "data_parallel": trainer.dp_mode,
+                           "dp_barrier_timed_out": bool(getattr(trainer.gen_opt, "timed_out", lambda: False)()),
                            "l2": "no flush: per-step working set (params+grads+Adam state ~265 MB) exceeds the 126 MB L2"},
                 "e2e": {"value": world * bs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(h6.numel() * 4 + hm.numel() * 4 + 8), "d2h_bytes_per_step": 20},
