@@ -21,6 +21,11 @@
  *   hmvae_mse_*             seq_two_hier_sa_vae.py:430-434  l2_criterion
  *   hmvae_traj_*            trajectory_pred_model.py:289-303, 237-244  gen_motion_w_trajectory + 2x MSE
  *   hmvae_adam_step         trainer_motion_vae.py:29-31, 92-93  torch.optim.Adam(lr, weight_decay) step
+ *   hmvae_dp_adam_step      train_motion_vae.py:49-53 (nn.DataParallel) + trainer_motion_vae.py:29-31, 92-93: gradient
+ *                           reduce-scatter + Adam + parameter all-gather over NVLink peer memory, one kernel per rank
+ *   hmvae_linear_*          seq_two_hier_sa_vae.py:132-136, 159-164, 225-229, 267  latent nn.Linear heads
+ *   hmvae_batch_assemble,   utils_motion_vae.py:140-187 (MotionSeqData.__getitem__ arithmetic) and :17-57
+ *   hmvae_rand_rotation     (rand_rotation_matrix): the batch assembly right before the path
  */
 #ifndef HMVAE_B200_H
 #define HMVAE_B200_H
