@@ -50,6 +50,7 @@ struct TcArgs {
   int a_bytes, stage_bytes;
   int tmem_cols;
   int splits, split_len;   // split-K: gridDim.z CTAs per (tile, group), each handles split_len consecutive stages
+  int groups, dcols;       // joint groups (gridDim.y); accumulator columns per group (= GJ * n_pad) in the dump
   const struct TcWorkG* wtab;   // [groups] host-built work tables (device memory, owned by the plan)
 };
 
@@ -251,14 +252,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   const int mt = blockIdx.x;
   const int j0 = blockIdx.y * p.GJ;
   const int gj = (a.J - j0 < p.GJ) ? a.J - j0 : p.GJ;
-  // first sequence of the tile; with dgrad time tiling (Bt == 1) a sequence spans ntt tiles and a tile only owns result steps
-  // [u_lo, u_lo + ucnt) (fprop / untiled dgrad: all of them)
-  const int b0 = (p.ntt > 1) ? mt / p.ntt : mt * p.Bt;
-  const int tt = (p.ntt > 1) ? mt % p.ntt : 0;
-  const int t0 = tc_tile_t0(tt, p.ntt, p.U, a.p, p.T + 2 * a.p);
-  const int Tres = (p.mode == 0) ? p.T_out : p.T;
-  const int u_lo = (p.ntt > 1) ? tt * p.U : 0;
-  const int ucnt = (p.ntt > 1) ? ((Tres - u_lo < p.U) ? Tres - u_lo : p.U) : Tres;
   const int ncb = p.ck_pad / p.KC;
   const int qpb = p.KC / 4;
 
@@ -396,80 +389,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
     if (lane == 0) tc_commit(&accum_bar);
     __syncwarp();
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
-    const int pt = tid - 64;            // 0..127
+    // =============================== epilogue (warps 2..5): TMEM -> accumulator dump ===============================
+    // Every (tile, group, split) CTA dumps its raw fp32 accumulators row-major, dump[split][tile][group][128 rows][dcols]:
+    // a thread owns one accumulator row and writes 64 contiguous bytes per tcgen05.ld -- no shared-memory transpose, no index
+    // arithmetic per element (the old NCW-scattering epilogue was ~300 SASS instructions per element and dominated the life of a
+    // CTA at B=32).  Layout conversion, split-K sum, bias / LeakyReLU / pooling / reflect fold happen in conv_tc_finish_kernel.
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    float* outs = reinterpret_cast<float*>(smem_raw);          // [gj * n_real][128]   (stage buffers are free now)
     const int lq = warp & 3;
     const int m = lq * 32 + lane;
-    for (int jl = 0; jl < gj; ++jl) {
-      for (int c16 = 0; c16 < p.n_pad; c16 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(jl * p.n_pad + c16), v);
+    float4* drow = reinterpret_cast<float4*>(dst + ((((size_t)blockIdx.z * p.mtiles + mt) * p.groups + blockIdx.y) * 128 + m) * p.dcols);
+    const int ncols = gj * p.n_pad;
+    for (int c16 = 0; c16 < ncols; c16 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c16, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c16 + i < p.n_real) outs[(size_t)(jl * p.n_real + c16 + i) * 128 + m] = v[i];
-      }
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int nch = gj * p.n_real;
-    if (p.splits > 1) {
-      // partial sums: plain [split][B][J*n_real][Tr] layout (Tr = T_out for fprop, T for dgrad), finished by conv_tc_finish_kernel
-      const int Tr = (p.mode == 0) ? p.T_out : p.T;
-      float* part = dst + (size_t)blockIdx.z * p.B * a.J * p.n_real * Tr;
-      const int total = nch * p.Bt * ucnt;
-      for (int e = pt; e < total; e += 128) {
-        const int u = u_lo + e % ucnt;
-        const int r = e / ucnt;
-        const int b = r % p.Bt, ch = r / p.Bt;
-        if (b0 + b < p.B) {
-          float v;
-          if (p.mode == 0) {
-            v = outs[(size_t)ch * 128 + u * p.Bt + b];
-          } else {
-            const float* row = outs + (size_t)ch * 128 + b;
-            v = row[(u + a.p - t0) * p.Bt];
-            if (a.pad_mode == 1) {
-              if (u >= 1 && u <= a.p) v += row[(a.p - u - t0) * p.Bt];
-              if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += row[(a.p + 2 * (p.T - 1) - u - t0) * p.Bt];
-            }
-          }
-          part[((size_t)(b0 + b) * a.J * p.n_real + (size_t)j0 * p.n_real + ch) * Tr + u] = v;
-        }
-      }
-    } else if (p.mode == 0) {
-      const int total = nch * p.Bt * p.T_out;
-      for (int e = pt; e < total; e += 128) {
-        const int t = e % p.T_out;
-        const int r = e / p.T_out;
-        const int b = r % p.Bt, ch = r / p.Bt;
-        if (b0 + b < p.B) {
-          const int jl = ch / p.n_real, o = ch % p.n_real;
-          float v = outs[(size_t)ch * 128 + t * p.Bt + b] + (bias ? bias[(j0 + jl) * a.co + o] : 0.f);
-          if (a.lrelu) v = lrelu_f(v, 0.2f);
-          dst[tc_out_index(a, b0 + b, j0 + jl, o, t, p.T_out)] = v;
-        }
-      }
-    } else {
-      const int total = nch * p.Bt * ucnt;
-      const int Cin = a.J * a.ci;
-      for (int e = pt; e < total; e += 128) {
-        const int u = u_lo + e % ucnt;
-        const int r = e / ucnt;
-        const int b = r % p.Bt, ch = r / p.Bt;
-        if (b0 + b < p.B) {
-          const int jl = ch / p.n_real, c = ch % p.n_real;
-          const float* row = outs + (size_t)ch * 128 + b;
-          float v = row[(u + a.p - t0) * p.Bt];
-          if (a.pad_mode == 1) {
-            if (u >= 1 && u <= a.p) v += row[(a.p - u - t0) * p.Bt];
-            if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += row[(a.p + 2 * (p.T - 1) - u - t0) * p.Bt];
-          }
-          dst[((long)(b0 + b) * Cin + (j0 + jl) * a.ci + c) * p.T + u] = v;
-        }
-      }
+      for (int q = 0; q < 4; ++q) drow[(c16 >> 2) + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
   }
   // ---- teardown
@@ -480,9 +415,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   }
 }
 
-// ---------------------------------------------------------------------------------------------- split-K finish
-__global__ void conv_tc_finish_kernel(TcArgs p, const float* __restrict__ part, const float* __restrict__ bias,
-                                      float* __restrict__ dst) {
+// ---------------------------------------------------------------------------------------------- finish
+// Accumulator dump -> result tensor.  One thread per result element (time fastest, so the NCW stores coalesce):
+//   fprop: y[b, j, o, t]  = act(sum_z dump[z][tile(b)][group(j)][t*Bt + b'][jl*n_pad + o] + bias)
+//   dgrad: dx[b, n, c, u] = sum_z (row(u + p) + reflect-fold rows) of the same dump
+// The split-K partial sums are added in a fixed order (deterministic).
+__device__ __forceinline__ float tc_dump_sum(const TcArgs& p, const float* __restrict__ dump, int mt, int g, int row, int col) {
+  const size_t zstride = (size_t)p.mtiles * p.groups * 128 * p.dcols;
+  const float* d = dump + (((size_t)mt * p.groups + g) * 128 + row) * p.dcols + col;
+  float v = 0.f;
+  for (int z = 0; z < p.splits; ++z) v += d[z * zstride];
+  return v;
+}
+
+// fprop result before the activation: conv sum + bias of conv-output joint j, channel o, sequence b, step t
+__device__ __forceinline__ float tc_fprop_value(const TcArgs& p, const float* __restrict__ dump, const float* __restrict__ bias,
+                                                int b, int j, int o, int t) {
+  const int mt = b / p.Bt;
+  float v = tc_dump_sum(p, dump, mt, j / p.GJ, t * p.Bt + (b - mt * p.Bt), (j % p.GJ) * p.n_pad + o);
+  if (bias) v += bias[j * p.a.co + o];
+  return v;
+}
+
+// dgrad result: gradient w.r.t. the (virtual) conv input of joint n, channel c, sequence b, step u (padding adjoint folded in)
+__device__ __forceinline__ float tc_dgrad_value(const TcArgs& p, const float* __restrict__ dump, int b, int n, int c, int u) {
+  const ConvArgs& a = p.a;
+  int mt, bl, t0 = 0;
+  if (p.ntt > 1) {
+    const int tt = u / p.U;
+    mt = b * p.ntt + tt;
+    bl = 0;
+    t0 = tc_tile_t0(tt, p.ntt, p.U, a.p, p.T + 2 * a.p);
+  } else {
+    mt = b / p.Bt;
+    bl = b - mt * p.Bt;
+  }
+  const int g = n / p.GJ, col = (n % p.GJ) * p.n_pad + c;
+  float v = tc_dump_sum(p, dump, mt, g, (u + a.p - t0) * p.Bt + bl, col);
+  if (a.pad_mode == 1) {
+    if (u >= 1 && u <= a.p) v += tc_dump_sum(p, dump, mt, g, (a.p - u - t0) * p.Bt + bl, col);
+    if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += tc_dump_sum(p, dump, mt, g, (a.p + 2 * (p.T - 1) - u - t0) * p.Bt + bl, col);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) conv_tc_finish_kernel(TcArgs p, const float* __restrict__ dump, const float* __restrict__ bias,
+                                                             float* __restrict__ dst) {
   pdl_trigger();
   pdl_wait();
   const ConvArgs& a = p.a;
@@ -490,19 +468,17 @@ __global__ void conv_tc_finish_kernel(TcArgs p, const float* __restrict__ part, 
   const int C = a.J * p.n_real;
   const long per = (long)p.B * C * Tr;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (long)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    for (int z = 0; z < p.splits; ++z) v += part[z * per + e];
+    const int t = (int)(e % Tr);
+    const long r = e / Tr;
+    const int ch = (int)(r % C);
+    const int b = (int)(r / C);
+    const int j = ch / p.n_real, o = ch - j * p.n_real;
     if (p.mode == 0) {
-      const int t = (int)(e % Tr);
-      const long r = e / Tr;
-      const int ch = (int)(r % C);
-      const long b = r / C;
-      const int j = ch / p.n_real, o = ch % p.n_real;
-      if (bias) v += bias[ch];
+      float v = tc_fprop_value(p, dump, bias, b, j, o, t);
       if (a.lrelu) v = lrelu_f(v, 0.2f);
       dst[tc_out_index(a, b, j, o, t, p.T_out)] = v;
     } else {
-      dst[e] = v;
+      dst[e] = tc_dgrad_value(p, dump, b, j, o, t);
     }
   }
 }
@@ -681,6 +657,8 @@ static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mod
   p.Tt = (mode == 0) ? p.T_out : Tq;
   p.n_real = L.n_real; p.n_pad = L.n_pad; p.ck = L.ck; p.ck_pad = L.ck_pad; p.KC = L.KC; p.GJ = L.GJ; p.nbmax = L.nbmax;
   p.wtab = L.dev_work;
+  p.groups = L.groups;
+  p.dcols = L.GJ * L.n_pad;
   p.ntt = 1;
   p.U = (mode == 0) ? p.T_out : T;
   if (p.Tt < 1) return false;
@@ -755,9 +733,8 @@ bool conv_tc_supported(const hmvae_conv_plan* plan, int B, int T, int mode) {
 }
 
 static long tc_stage_ws(const TcArgs& p) { return (long)p.mtiles * p.a.J * (p.ck_pad / p.KC) * p.a_bytes; }
-static long tc_part_ws(const TcArgs& p) {
-  if (p.splits <= 1) return 0;
-  return (long)p.splits * p.B * p.a.J * p.n_real * (p.mode == 0 ? p.T_out : p.T) * 4;
+static long tc_part_ws(const TcArgs& p) {      // accumulator dump [splits][mtiles][groups][128][dcols]
+  return (long)p.splits * p.mtiles * p.groups * 128 * p.dcols * 4;
 }
 
 long conv_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T, int mode) {
@@ -802,16 +779,12 @@ int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, cons
     int rc = check_launch("conv_tc_prep");
     if (rc) return rc;
   }
-  size_t smem = (size_t)p.stages * p.stage_bytes;
-  const size_t epi = (size_t)p.GJ * p.n_real * 128 * 4;      // the epilogue's transpose buffer reuses the stage ring
-  if (epi > smem) smem = epi;
-  smem += 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(p.mtiles, (p.a.J + p.GJ - 1) / p.GJ, p.splits);
-  launch_pdl<true>(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, p, reinterpret_cast<const unsigned char*>(workspace), wp, bias,
-             p.splits > 1 ? part : dst);
+  dim3 grid(p.mtiles, p.groups, p.splits);
+  launch_pdl<true>(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, p, reinterpret_cast<const unsigned char*>(workspace), wp, bias, part);
   int rc = check_launch(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
-  if (rc || p.splits <= 1) return rc;
+  if (rc) return rc;
   const long per = (long)p.B * p.a.J * p.n_real * (mode == 0 ? p.T_out : p.T);
   long blocks = (per + 255) / 256, cap = (long)num_sms() * 8;
   launch_pdl(conv_tc_finish_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, (const float*)part, bias, dst);

@@ -82,7 +82,7 @@ def test_fk_golden_fwd_bwd(fk, golden_modules):
     np.testing.assert_allclose(pos.cpu().numpy(), g["fkp_pos"], rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("n", [0, 1, 43, 683, 10923])
+@pytest.mark.parametrize("n", [0, 1, 43, 683, 10923, 174763])
 @pytest.mark.parametrize("six", [False, True])
 def test_fk_vs_oracle_sweep(fk, smpl, n, six):
     if n == 0:
@@ -194,17 +194,13 @@ LAYER_SHAPES = [  # (level, ci, co, K, stride, T_in, upsample, unpool_level)  --
 ]
 
 
-@pytest.mark.parametrize("shape", LAYER_SHAPES)
-@pytest.mark.parametrize("impl", ["simt", "auto"])
-def test_conv_layer_shapes_vs_oracle(golden_topology, shape, impl):
-    """Every conv geometry of the shipped configs, with the fused prologue (upsample + unpool) and LeakyReLU epilogue."""
+def _conv_layer_case(golden_topology, shape, impl, b):
     lvl, ci, co, k, s, t_in, up, unpool_lvl = shape
     ops.set_conv_impl(ops.IMPL_SIMT if impl == "simt" else ops.IMPL_AUTO)
     tol = 1e-5 if impl == "simt" else 2e-3
     topo = golden_topology["levels"]
     nb = topo[lvl]["neighbours"]
     j = len(nb)
-    b = 5
     torch.manual_seed(lvl * 100 + k)
     conv = H.SkeletonConv(nb, j * ci, j * co, k, j, stride=s, padding=(k - 1) // 2, bias=True, padding_mode="reflection")
     w, bias, mask = conv.weight.detach().clone(), conv.bias.detach().clone(), conv.mask.detach().clone()
@@ -225,6 +221,10 @@ def test_conv_layer_shapes_vs_oracle(golden_topology, shape, impl):
         ref_in = xr
         xm = x.to(DEV).requires_grad_(True)
         y = conv.fused_forward(xm, lrelu=True)
+    if impl != "simt":
+        # the tensor-core kernels really ran for every pass of this geometry (a silent CUDA-core fallback would pass trivially)
+        plan = conv.plan(upsample=True, unpool_src=un.src, src_joints=src_j, lrelu=True) if unpool_lvl is not None else conv.plan(lrelu=True)
+        assert ops._tc_ok(plan, b, t_in, 0) and ops._tc_ok(plan, b, t_in, 1), "tcgen05 path does not cover %r at b=%d" % (shape, b)
     wr, br = w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
     z_ref = O.skeleton_conv(ref_in, wr, mask, br, s, (k - 1) // 2, "reflection")
     ref = torch.nn.functional.leaky_relu(z_ref, 0.2)
@@ -238,7 +238,29 @@ def test_conv_layer_shapes_vs_oracle(golden_topology, shape, impl):
     assert rel_l2(xm.grad.cpu(), xr.grad) < tol
     assert rel_l2(conv.weight.grad.cpu(), wr.grad) < tol
     assert rel_l2(conv.bias.grad.cpu(), br.grad) < tol
+    assert float((conv.weight.grad * (1 - conv.mask)).abs().sum()) == 0.0
     ops.set_conv_impl(ops.IMPL_AUTO)
+
+
+@pytest.mark.parametrize("shape", LAYER_SHAPES)
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_conv_layer_shapes_vs_oracle(golden_topology, shape, impl):
+    """Every conv geometry of the shipped configs, with the fused prologue (upsample + unpool) and LeakyReLU epilogue."""
+    _conv_layer_case(golden_topology, shape, impl, 5)
+
+
+@pytest.mark.parametrize("shape", LAYER_SHAPES)
+def test_conv_layer_shapes_benchmarked_batch(golden_topology, shape):
+    """The same geometries at the BENCHMARKED batch (B=32 per GPU; B=8 for the len8 / trajectory layers): batch packing of the M
+    tiles, split-K and multi-tile grids -- fprop, dgrad, wgrad and dbias at 2e-3 on the tensor-core path."""
+    b = 32 if shape[3] == 15 else 8
+    _conv_layer_case(golden_topology, shape, "auto", b)
+
+
+@pytest.mark.parametrize("shape", LAYER_SHAPES[:8])
+def test_conv_layer_shapes_b512(golden_topology, shape):
+    """BASELINE config 4 batch (B=512): 256+ M tiles per layer, all three passes at 2e-3."""
+    _conv_layer_case(golden_topology, shape, "auto", 512)
 
 
 def test_conv_reflect_pad_too_large_is_an_error(golden_topology):
@@ -386,6 +408,27 @@ def test_hmvae_full_batch_vs_oracle(smpl, impl):
             continue
         assert rel_l2(p.grad.cpu(), ora.params[k].grad) < gtol, k
     ops.set_conv_impl(ops.IMPL_AUTO)
+
+
+def test_hmvae_test_path_b512_vs_oracle(smpl):
+    """BASELINE config 4: `test()` at B=512 (1 encoder + 2 decoder passes + 3 FK, no grad) against the oracle restatement of
+    seq_two_hier_sa_vae.py:560-639 -- joint positions within 2e-3 relative-L2 on the tensor-core path."""
+    parents, off = smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])
+    ora = O.HMVAEOracle(HP64, parents, off).init(seed=0)
+    model = _load(TwoHierSAVAEModel(dict(HP64), device=DEV), ora)
+    bs = 512
+    batch = O.synthetic_batch(bs, 64, parents, off, seed=99)
+    gen = torch.Generator().manual_seed(5)
+    ks = [len(p) for p in model.enc.pooling_list]
+    lat = [model.shallow_latent_d] + [model.latent_d] * (len(ks) - 1)
+    zs = [torch.randn(bs, k, d, generator=gen) for k, d in zip(ks, lat)]
+    gt_r, mean_r, samp_r = ora.test_path(batch["seq_rot_6d"], batch["seq_rot_mat"], zs)
+    hp2 = dict(HP64, random_root_rot_flag=False)
+    gt, mean, samp, _ = model.test((batch["seq_rot_6d"], batch["seq_rot_mat"]), hp2, 0, sampled_z_list=[z.to(DEV) for z in zs])
+    assert gt.shape == (64, bs, 24, 3)
+    assert rel_l2(gt.cpu(), gt_r) < 1e-5
+    assert rel_l2(mean.cpu(), mean_r) < 2e-3
+    assert rel_l2(samp.cpu(), samp_r) < 2e-3
 
 
 @pytest.mark.parametrize("impl", ["simt", "auto"])
