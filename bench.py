@@ -26,6 +26,14 @@ import yaml  # noqa: E402
 METRIC, UNIT = "train_sequences_per_sec", "sequences/s"
 
 
+def workload_config(bs, world):
+    """`config` of the JSON line -- IDENTICAL in both arms (the driver compares them)."""
+    return {"workload": "configs/len64_no_aug_hm_vae.yaml train step (fwd+bwd+allreduce+Adam), B=%d per GPU, T=64, 24-joint SMPL, "
+                        "random-init weights" % bs,
+            "global_batch": world * bs, "parallelism": "dp%d" % world,
+            "l2": "no flush: per-step working set (params+grads+Adam state ~265 MB) exceeds the 126 MB L2"}
+
+
 def load_cfg(name):
     return yaml.safe_load(open(os.path.join(ROOT, "configs", name)))
 
@@ -105,18 +113,134 @@ def run_reference(args, hp):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 20), min(max(args.warmup, 1), 3)
+    # same --steps / --warmup as the product arm (>= 3 warm-up like there); one step is ~0.15 s on 16 host cores, so the run is
+    # bounded by capping the timed steps at 600 (~90 s)
+    steps, warmup = min(args.steps, 600), max(args.warmup, 3)
     sec, threads = cpu_reference_step_time(hp, args.batch, steps, warmup)
     value = args.batch / sec
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "len64_no_aug_hm_vae train step (fwd+bwd+Adam), B=%d, T=64, 24-joint SMPL" % args.batch},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.batch, 1),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d timed steps of B=%d after %d warm-up (oracle/hmvae_ref.py, torch CPU fp32)" % (steps, args.batch, warmup)},
+                             "sample": "%d timed steps of B=%d after %d warm-up (oracle/hmvae_ref.py, torch CPU fp32, fwd+bwd+Adam)" % (steps, args.batch, warmup)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ reference on the same GPU
+def reference_cuda_leg(hp, batch, dev, steps=30, warmup=5):
+    """SURVEY 8(d) "reference timing alongside (i)": the reference's own CUDA-PyTorch path on this B200 -- eager torch ops
+    (F.conv1d on weight*mask through cuDNN, matmul pool / unpool, nn.Upsample, the 23-step FK chain, autograd backward,
+    torch.optim.Adam), cudnn.benchmark=True and torch's default TF32 policy as in train_motion_vae.py:16-18.  /root/reference
+    does not exist on the GPU box, so this is the oracle port (op-for-op restatement, pinned against the real reference by
+    tests/test_oracle_golden.py) moved to the device: kind = "port".  It is a measured baseline, never the product path."""
+    from oracle import hmvae_ref as O
+
+    was = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        d = np.load(os.path.join(ROOT, "hm_vae_b200", "data", "smpl24.npz"))
+        parents, off = d["parents"].tolist(), torch.from_numpy(d["offsets"])
+        ora = O.HMVAEOracle(hp, parents, off).init(seed=0)
+        ora.set_params({k: v.detach() for k, v in ora.params.items()}, device=dev)
+        opt = torch.optim.Adam(list(ora.params.values()), lr=hp["lr"], weight_decay=hp["weight_decay"])
+        data = O.synthetic_batch(batch, hp["train_seq_len"], parents, off, seed=1234, device=dev)
+        eps = O.draw_eps(ora, batch, seed=4321, device=dev)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            out = ora.step(data["seq_rot_6d"], data["seq_rot_mat"], eps, iterations=0)
+            opt.step()
+            return out
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / steps
+        return {"kind": "port", "what": "reference algorithm as eager CUDA-PyTorch ops on this GPU (oracle/hmvae_ref.py on cuda: cuDNN conv1d "
+                                        "on weight*mask, autograd, torch.optim.Adam; cudnn.benchmark=True, default TF32 policy)",
+                "ms_per_step": ms, "sequences_per_s": batch / (ms * 1e-3), "steps": steps, "warmup": warmup, "batch": batch,
+                "loss": float(out["total"])}
+    finally:
+        torch.backends.cudnn.benchmark = was
+
+
+def measure_tf32_peak(dev, n=8192, iters=10):
+    """cuBLAS TF32 GEMM n^3 (allow_tf32), best of `iters` -- the conv roofline denominator ("to be measured")."""
+    was = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b)
+        best = None
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        del a, b
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = was
+
+
+def other_configs_leg(dev):
+    """BASELINE config 2 (len8, B=8: launch-overhead bound) and the config-5 trajectory model (T=128, K=31, B=8): training step
+    through Trainer.gen_update as a CUDA graph (parity for both: tests/test_gpu_parity.py)."""
+    from hm_vae_b200 import ops
+    from hm_vae_b200.trainer_motion_vae import Trainer
+
+    def timed(fn, steps):
+        for _ in range(5):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def hmvae_data(hp, bs):
+        return synthetic_device_batch(bs, hp["train_seq_len"], dev, 1234)
+
+    def traj_data(hp, bs):
+        T = hp["train_seq_len"]
+        g = torch.Generator().manual_seed(1234)
+        d6, dm = hmvae_data(hp, bs)
+        return (d6, dm, None, torch.randn(bs, T, 72, generator=g).to(dev), None, None, torch.randn(bs, T, 3, generator=g).to(dev))
+
+    out = {}
+    for tag, cfg_name, bs, make in (("len8", "len8_data_aug_hm_vae.yaml", 8, hmvae_data), ("trajectory", "trajectory_model.yaml", 8, traj_data)):
+        try:
+            hp = load_cfg(cfg_name)
+            torch.manual_seed(0)
+            tr = Trainer(dict(hp), device=dev, sync_losses=False).to(dev)
+            data = make(hp, bs)
+            tr.enable_cuda_graph(data, hp, 0, warmup=3)
+            ms = timed(lambda: tr.gen_update(data, hp, 0), 100)
+            res = tr.gen_update(data, hp, 0)
+            out[tag] = {"config": "configs/" + cfg_name, "batch": bs, "ms_per_step": ms, "sequences_per_s": bs / (ms * 1e-3),
+                        "launches_per_step": tr.launches_per_step, "loss": float(res[0]), "cuda_graph": True}
+            tr.gen_opt.close()
+            del tr
+        except Exception as exc:        # reported, never fatal for the headline line
+            out[tag] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ kernel instrumentation
@@ -233,7 +357,7 @@ def inference_leg(model, hp, dev, pk, batch=512, iters=10):
     tf = fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
     return {"workload": "configs/len_64_test_interpolation.yaml test() path, B=%d, no grad, eager" % batch, "ms_per_call": ms,
             "sequences_per_s": batch / (ms * 1e-3), "conv_fprop_ms": conv_ms, "conv_algorithmic_gflop": fl / 1e9,
-            "conv_tflops": tf, "conv_frac_of_tf32_peak": (tf / (pk["bf16"] / 2.0)) if tf else None,
+            "conv_tflops": tf, "conv_frac_of_tf32_peak": (tf / pk["tf32"]) if tf else None, "tf32_peak_tflops": pk["tf32"],
             "conv_us_per_layer": kt.per_layer(2)}
 
 
@@ -250,7 +374,7 @@ def synthetic_device_batch(bs, t, dev, seed):
     return seq_rot_6d, seq_rot_mat
 
 
-def fk_sweep(dev, pk, sizes=(10923, 174763, 699051), iters=20):
+def fk_sweep(dev, pk, sizes=(43, 683, 10923, 174763, 699051), iters=20):
     """BASELINE config 3: FK and rot6d->R, fwd and bwd kernels timed through the C ABI (no autograd glue), achieved
     algorithmic GB/s (FK 48 / 84 B per joint-frame, rot6d 60 / 84).  The largest size is the headline."""
     from hm_vae_b200 import _lib
@@ -294,8 +418,11 @@ def fk_sweep(dev, pk, sizes=(10923, 174763, 699051), iters=20):
     big = out["sizes"][str(sizes[-1])]
     out.update(frames=sizes[-1], fwd_gbs=big["fk_fwd"]["gbs"], bwd_gbs=big["fk_bwd"]["gbs"], fwd_frac=big["fk_fwd"]["frac"],
                bwd_frac=big["fk_bwd"]["frac"], peak_gbs=pk["hbm"],
+               fwd_bwd_gbs=round((48.0 + 84.0) * sizes[-1] * 24 / ((big["fk_fwd"]["us"] + big["fk_bwd"]["us"]) * 1e-6) / 1e9, 1),
                note="kernel time through the C ABI, CUDA events, %d back-to-back launches; algorithmic bytes 48 B/jf fwd, 84 B/jf bwd; "
-                    "the largest size moves 805 MB fwd / 1.4 GB bwd per launch (> 126 MB L2)" % iters)
+                    "the largest size moves 805 MB fwd / 1.4 GB bwd per launch (> 126 MB L2); the 43- and 683-frame sizes (1 K / 16 K "
+                    "joint-frames) are launch-latency bound: read their `us`, not their GB/s" % iters)
+    out["fwd_bwd_frac"] = round(out["fwd_bwd_gbs"] / pk["hbm"], 4)
     return out
 
 
@@ -311,6 +438,9 @@ def run_b200(args, hp):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     pk = peaks()
+    # TF32 dense peak: measured here (cuBLAS TF32 8192^3 burst) -- the conv roofline denominator
+    pk["tf32"] = measure_tf32_peak(dev) if rank == 0 else pk["bf16"] / 2.0
+    pk["tf32_src"] = "measured in this run: torch.matmul 8192^3 with allow_tf32 (cuBLAS TF32), best of 10, CUDA events"
     ops.set_conv_impl({"auto": 0, "simt": 1, "tc": 2}[args.conv_impl])
 
     torch.manual_seed(0)
@@ -426,7 +556,7 @@ def run_b200(args, hp):
         top = max(cls_ms, key=lambda k: cls_ms[k])
         top_ms = cls_ms[top]
         achieved = fl_fwd / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
-        tf32_peak = pk["bf16"] / 2.0
+        tf32_peak = pk["tf32"]
         total_kernel_ms = sum(v["ms"] for v in summ.values()) / prof_steps
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -436,10 +566,11 @@ def run_b200(args, hp):
         roofline = {"kernel": "hmvae_conv_%s%s (all %d layers of one step = one launch set)" % (top, "" if args.conv_impl == "simt" else "_tc", n_layers),
                     "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": achieved / tf32_peak, "traffic": traffic,
-                    "peak_note": "TF32 dense taken as 1/2 of the %s bf16 burst figure (%.1f TF/s); conv math is %s.  At B=32 the layers "
+                    "peak_note": "TF32 dense peak %s (for scale: %s bf16 burst %.1f TF/s); conv math is %s.  At B=32 the layers "
                                  "are latency / weight-bandwidth bound (7.2 GFLOP and 41 MB of weights per pass): see conv_large_batch for "
                                  "the tensor-bound regime" % (
-                        pk["src"], pk["bf16"], "fp32 CUDA-core" if args.conv_impl == "simt" else "auto (tcgen05 TF32 where supported, else fp32 CUDA-core)"),
+                        pk["tf32_src"], pk["src"], pk["bf16"],
+                        "fp32 CUDA-core" if args.conv_impl == "simt" else "auto (tcgen05 TF32 where supported, else fp32 CUDA-core)"),
                     "algorithmic_flops_per_launch_set": fl_fwd,
                     "ms_per_launch_set": top_ms,
                     "conv_class_ms_per_step": {k: round(v, 4) for k, v in cls_ms.items()},
@@ -461,19 +592,28 @@ def run_b200(args, hp):
             sec, threads = cpu_reference_step_time(hp, bs, 60, 3)
             cpu = {"value": bs / sec, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "60 timed steps of B=%d after 3 warm-up (oracle/hmvae_ref.py, torch CPU fp32, fwd+bwd+Adam)" % bs}
+        ref_cuda = others = None
+        if args.reference_cuda and world == 1:
+            try:
+                ref_cuda = reference_cuda_leg(hp, bs, dev)
+                ref_cuda["speedup_value"] = (bs / (ms * 1e-3)) / ref_cuda["sequences_per_s"]
+                ref_cuda["speedup_e2e"] = (bs / (ms_e2e * 1e-3)) / ref_cuda["sequences_per_s"]
+            except Exception as exc:
+                ref_cuda = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        if args.other_configs and world == 1:
+            others = other_configs_leg(dev)
+        cfg = workload_config(bs, world)
         line = {"metric": METRIC, "value": world * bs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "tf32" if args.conv_impl != "simt" else "f32", "data": "synthetic",
-                "config": {"workload": "configs/len64_no_aug_hm_vae.yaml train step (fwd+bwd+allreduce+Adam), B=%d per GPU, "
-                                       "T=64, 24-joint SMPL, random-init weights" % bs,
-                           "global_batch": world * bs, "parallelism": "dp%d" % world, "cuda_graph": bool(args.graph),
-                           "conv_impl": args.conv_impl, "data_parallel": trainer.dp_mode,
-                           "dp_barrier_timed_out": bool(getattr(trainer.gen_opt, "timed_out", lambda: False)()),
-                           "l2": "no flush: per-step working set (params+grads+Adam state ~265 MB) exceeds the 126 MB L2"},
+                "config": cfg,
+                "run": {"cuda_graph": bool(args.graph), "conv_impl": args.conv_impl, "data_parallel": trainer.dp_mode,
+                        "dp_barrier_timed_out": bool(getattr(trainer.gen_opt, "timed_out", lambda: False)())},
                 "e2e": {"value": world * bs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(h6.numel() * 4 + hm.numel() * 4 + 8), "d2h_bytes_per_step": 20},
                 "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
-                "clocks": clocks, "roofline": roofline, "fk": fk, "conv_large_batch": big, "cpu_baseline": cpu, "loss": loss_val}
+                "clocks": clocks, "roofline": roofline, "fk": fk, "conv_large_batch": big, "cpu_baseline": cpu,
+                "reference_cuda": ref_cuda, "other_configs": others, "loss": loss_val}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -495,6 +635,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-fk-sweep", dest="fk_sweep", action="store_false")
     ap.add_argument("--no-large-batch", dest="large_batch", action="store_false")
+    ap.add_argument("--no-reference-cuda", dest="reference_cuda", action="store_false")
+    ap.add_argument("--no-other-configs", dest="other_configs", action="store_false")
     args = ap.parse_args()
     hp = load_cfg("len64_no_aug_hm_vae.yaml")
     if args.impl == "reference":

@@ -310,6 +310,146 @@ __global__ void __launch_bounds__(32) fk_bwd_kernel(const float* __restrict__ ro
   if (BULK) bulk_wait_all();
 }
 
+// ------------------------------------------------------------------------------------------------ FK backward, row-split
+// The lane-per-frame kernel above is a ~3 400-instruction dependent chain per 32-frame tile with 54 KB of staging per warp:
+// four warps per SM, each issuing every ~7 cycles (ncu, profiles/r01_fk_details.txt) => 35 % of the HBM roofline.  This variant
+// splits every frame over THREE lanes.  All quantities of the chain decompose by the row r of the global rotation:
+//     Rg_i[r,:] = Rg_p[r,:] R_i                        (forward recomputation)
+//     S_i[r]    = dpos_i[r] + sum_children S_c[r]       (accumulated position gradient)
+//     H_p[r,:] += S_i[r] off_i^T + H_i[r,:] R_i^T      (gradient w.r.t. the global rotation of the parent)
+// so lane (f, r) walks the whole tree for frame f with one third of the arithmetic and one third of the live registers; only
+//     dR_i = Rg_p^T H_i                                 (row t of dR_i = sum_u Rg_p[u,t] H_i[u,:])
+// mixes rows: the three lanes of a frame exchange H_i (6 shuffles) and one column element of Rg_p each (2 shuffles) and every
+// lane writes one row of dR_i in place of R_i.  A warp owns 10 consecutive frames (lanes 30, 31 shadow frame 9), i.e. 11.8 KB of
+// staging, so 16 warps per SM are resident and the bulk copies of one warp hide under the arithmetic of the others.
+constexpr int FKR_FRAMES = 10;
+constexpr int FKR_WARPS = 4;
+
+template <class Tree>
+__global__ void __launch_bounds__(32 * FKR_WARPS, 4) fk_bwd_rows_kernel(const float* __restrict__ rot, const float* __restrict__ offsets,
+                                                                         const float* __restrict__ dpos, float* __restrict__ drot,
+                                                                         long n, TreeTable tab) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ uint64_t bars[FKR_WARPS];
+  __shared__ TreeTable stab;
+  __shared__ float s_off[3 * FK_MAX_J];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int JM = Tree::JMAX;
+  Tree tr;
+  if constexpr (!Tree::kStatic) {
+    if (threadIdx.x == 0) stab = tab;
+    tr.t = &stab;
+  }
+  if (lane == 0) {
+    mbar_init(&bars[warp], 1);
+    mbar_fence_init();
+  }
+  for (int e = threadIdx.x; e < 3 * tab.J; e += blockDim.x) s_off[e] = offsets[e];
+  __syncthreads();
+  const int J = tr.joints();
+  const int rin = 9 * J, pitch_in = pad_pitch(rin);
+  const int rp = 3 * J, pitch_p = pad_pitch(rp);
+  float* s_in = smem + (size_t)warp * FKR_FRAMES * (pitch_in + pitch_p);
+  float* s_dp = s_in + FKR_FRAMES * pitch_in;
+  uint64_t* bar = &bars[warp];
+
+  const int f = lane < 3 * FKR_FRAMES ? lane / 3 : FKR_FRAMES - 1;      // frame inside the tile
+  const int r = lane < 3 * FKR_FRAMES ? lane - 3 * f : lane - 3 * FKR_FRAMES;   // row of the global rotation handled by this lane
+  const int base = 3 * f;
+  const int src1 = base + (r + 1) % 3, src2 = base + (r + 2) % 3;       // the other two lanes of the frame
+  uint32_t parity = 0;
+  const long ntiles = (n + FKR_FRAMES - 1) / FKR_FRAMES;
+  for (long tile = (long)blockIdx.x * FKR_WARPS + warp; tile < ntiles; tile += (long)gridDim.x * FKR_WARPS) {
+    const long f0 = tile * FKR_FRAMES;
+    const int nvalid = (int)((n - f0) < FKR_FRAMES ? (n - f0) : FKR_FRAMES);
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)nvalid * (rin + rp) * 4);
+    __syncwarp();
+    if (lane < nvalid) {
+      bulk_g2s(s_in + lane * pitch_in, rot + (f0 + lane) * rin, rin * 4, bar);
+      bulk_g2s(s_dp + lane * pitch_p, dpos + (f0 + lane) * rp, rp * 4, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+
+    float* row = s_in + f * pitch_in;
+    const float* drow = s_dp + f * pitch_p;
+    const bool writer = lane < 3 * FKR_FRAMES && f < nvalid;
+    // ---- pass 1: row r of every global rotation that has children
+    float Rg[JM][3];
+#pragma unroll
+    for (int i = 0; i < JM; ++i) {
+      if (i < J && (!Tree::kStatic || !tr.leaf(i))) {
+        float R[9];
+        row_load<9>(row, 9 * i, R);
+        if (i == 0) {
+          Rg[0][0] = r == 0 ? R[0] : (r == 1 ? R[3] : R[6]);
+          Rg[0][1] = r == 0 ? R[1] : (r == 1 ? R[4] : R[7]);
+          Rg[0][2] = r == 0 ? R[2] : (r == 1 ? R[5] : R[8]);
+        } else {
+          const int p = tr.parent(i);
+#pragma unroll
+          for (int b = 0; b < 3; ++b) Rg[i][b] = Rg[p][0] * R[b] + Rg[p][1] * R[3 + b] + Rg[p][2] * R[6 + b];
+        }
+      }
+    }
+    // ---- pass 2: reverse accumulation (row r of H, component r of S)
+    float H[JM][3], S[JM];
+#pragma unroll
+    for (int i = 0; i < JM; ++i) {
+      H[i][0] = H[i][1] = H[i][2] = 0.f;
+      S[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = JM - 1; i >= 0; --i) {
+      if (i < J) {
+        float d[3] = {0.f, 0.f, 0.f};
+        if (i == 0) {
+          d[0] = H[0][0]; d[1] = H[0][1]; d[2] = H[0][2];
+        } else {
+          const int p = tr.parent(i);
+          const float g = drow[3 * i + r] + S[i];
+          S[p] += g;
+#pragma unroll
+          for (int b = 0; b < 3; ++b) H[p][b] += g * s_off[3 * i + b];
+          if (!tr.leaf(i)) {
+            float R[9];
+            row_load<9>(row, 9 * i, R);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) H[p][b] += H[i][0] * R[3 * b] + H[i][1] * R[3 * b + 1] + H[i][2] * R[3 * b + 2];
+            // row r of dR_i = sum_u Rg_p[u][r] * H_i[u][:]
+            // what the OTHER lanes need from me: lane t = (r + 2) % 3 reads me as its src1 and wants Rg_p[r][t]; lane (r + 1) % 3
+            // reads me as its src2 and wants Rg_p[r][(r + 1) % 3]
+            const float own = r == 0 ? Rg[p][0] : (r == 1 ? Rg[p][1] : Rg[p][2]);
+            const float for_src1_reader = r == 0 ? Rg[p][2] : (r == 1 ? Rg[p][0] : Rg[p][1]);      // element (r + 2) % 3
+            const float for_src2_reader = r == 0 ? Rg[p][1] : (r == 1 ? Rg[p][2] : Rg[p][0]);      // element (r + 1) % 3
+            const float c1 = __shfl_sync(0xffffffffu, for_src1_reader, src1);
+            const float c2 = __shfl_sync(0xffffffffu, for_src2_reader, src2);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              const float h1 = __shfl_sync(0xffffffffu, H[i][b], src1);
+              const float h2 = __shfl_sync(0xffffffffu, H[i][b], src2);
+              d[b] = own * H[i][b] + c1 * h1 + c2 * h2;
+            }
+          }
+        }
+        __syncwarp();      // every lane of the frame has read R_i: its slot now receives dR_i
+        if (writer) {
+          row[9 * i + 3 * r] = d[0];
+          row[9 * i + 3 * r + 1] = d[1];
+          row[9 * i + 3 * r + 2] = d[2];
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane < nvalid) bulk_s2g(drot + (f0 + lane) * rin, s_in + lane * pitch_in, rin * 4);
+    bulk_commit();
+    bulk_wait_read_all();      // the rows are reused by the next tile
+    __syncwarp();
+  }
+  bulk_wait_all();
+}
+
 // ------------------------------------------------------------------------------------------------ rot6d / aa
 constexpr int ROT_TPB = 256;
 
@@ -513,6 +653,22 @@ static int launch_fk_bwd(const float* rot, const float* offsets, const float* po
   return check_launch("fk_bwd");
 }
 
+template <class Tree>
+static int launch_fk_bwd_rows(const float* rot, const float* offsets, const float* dpos, float* drot, long n, const TreeTable& tab,
+                              cudaStream_t st) {
+  const int J = tab.J;
+  const size_t bytes = (size_t)FKR_WARPS * FKR_FRAMES * (pad_pitch(9 * J) + pad_pitch(3 * J)) * 4;
+  auto k = fk_bwd_rows_kernel<Tree>;
+  int rc = set_smem(k, bytes);
+  if (rc) return rc;
+  const long tiles = (n + FKR_FRAMES - 1) / FKR_FRAMES;
+  long blocks = (tiles + FKR_WARPS - 1) / FKR_WARPS;
+  const long cap = (long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  k<<<(int)blocks, 32 * FKR_WARPS, bytes, st>>>(rot, offsets, dpos, drot, n, tab);
+  return check_launch("fk_bwd");
+}
+
 }  // namespace hmvae
 
 using namespace hmvae;
@@ -559,6 +715,12 @@ extern "C" int hmvae_fk_bwd(const float* rot, int rot_dim, const float* offsets,
   cudaStream_t st = (cudaStream_t)stream;
   const bool al = aligned16(rot) && aligned16(dpos) && aligned16(drot) && (!positions || aligned16(positions));
   const bool in6 = rot_dim == 6, pf = positions != nullptr;
+  // rotation-matrix input with the layer's own offsets (the training / benchmark case): three lanes per frame
+  // (bulk copies of whole frame rows: 9*J*4 and 3*J*4 bytes must be multiples of 16)
+  if (!in6 && !pf && al && joints % 4 == 0 && env_int("HMVAE_FK_BWD_ROWS", 1)) {
+    if (smpl) return launch_fk_bwd_rows<Smpl24Tree>(rot, offsets, dpos, drot, n, tab, st);
+    return launch_fk_bwd_rows<RuntimeTree>(rot, offsets, dpos, drot, n, tab, st);
+  }
   if (smpl && al) {
 #define BWD_S(I6, PF) if (in6 == I6 && pf == PF) return launch_fk_bwd<Smpl24Tree, I6, PF, true>(rot, offsets, positions, dpos, drot, n, tab, st);
     BWD_S(false, false) BWD_S(false, true) BWD_S(true, false) BWD_S(true, true)
