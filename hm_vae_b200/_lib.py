@@ -17,15 +17,24 @@ class HmvaeError(RuntimeError):
     pass
 
 
-def _build_library():
+def _build_library(force=False):
     if os.environ.get("HMVAE_AUTOBUILD", "1") != "1":
         raise HmvaeError("libhmvae_b200.so is missing or stale: run `python -m hm_vae_b200.build` (nvcc, sm_100a)")
     import importlib.util
 
+    import fcntl
+
     spec = importlib.util.spec_from_file_location("_hmvae_build", os.path.join(_HERE, "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    mod.build()
+    # one builder at a time: the ranks of a torchrun job import this module concurrently
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale():
+                mod.build(force=force)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 def _stale():
@@ -109,6 +118,7 @@ _SIGS = {
     "hmvae_traj_fwdbwd": (c_int, [P, P, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, c_float, c_float, P, P, P]),
     "hmvae_adam_step": (c_int, [POINTER(AdamTensor), c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
     "hmvae_adam_step_dyn": (c_int, [POINTER(AdamTensor), c_int, P, c_float, c_float, c_float, c_float, c_float, P]),
+    "hmvae_opt_clock_tick": (c_int, [P, c_float, c_float, c_int, c_float, c_float, P, P]),
     "hmvae_rand_rotation": (c_int, [P, ctypes.c_double, P, c_long, P]),
     "hmvae_batch_assemble": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
     "hmvae_dp_adam_step": (c_int, [POINTER(DpPeers), P, P, POINTER(c_long), c_int, P, c_float, c_float, c_float, c_float, c_float, P, c_int, P]),
@@ -133,7 +143,7 @@ def _bind():
 try:
     lib = _bind()
 except AttributeError:                  # stale library from an older source tree: rebuild once, then fail loudly
-    _build_library()
+    _build_library(force=True)
     lib = _bind()
 
 

@@ -16,15 +16,15 @@
 //            waits, so a rank's kernel (hence its next forward pass / its next backward pass overwriting the gradient arena)
 //            cannot complete before all its peers are done with its memory.
 //   No NCCL call, no host synchronisation: the kernel is CUDA-graph capturable (the epoch lives in device memory).
-//   A waiter that sees no signal for HMVAE_DP_TIMEOUT_NS raises state[2] and carries on (results are then wrong, but the GPU
-//   never hangs); the host checks the flag.
+//   A waiter that sees no signal for HMVAE_DP_TIMEOUT_S seconds (default 120) raises state[2] and its CTA SKIPS the update: no
+//   stale or half-written peer gradient is ever applied, the GPU never hangs, and the host raises at its next health check
+//   (Trainer._check_health: every host sync, save(), every 500 steps).
 #include <string.h>
 
 #include "common.cuh"
 
 namespace hmvae {
 
-constexpr unsigned long long DP_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 
 struct DpArgs {
   int world, rank;
@@ -35,6 +35,7 @@ struct DpArgs {
   int nranges;
   const float* mc_grad;     // NVSwitch multicast mappings of the two arenas (NULL: unicast peer loads / stores)
   float* mc_param;
+  unsigned long long timeout_ns;
 };
 
 // NVLS: one load returns the sum over all ranks' copies (reduced inside the switch), one store lands in every rank's copy
@@ -64,11 +65,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 // waits until *flag >= epoch (wrap-safe signed difference); false on timeout
-__device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int epoch) {
+__device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int epoch, unsigned long long timeout_ns) {
   const unsigned long long t0 = globaltimer_ns();
   unsigned int spins = 0;
   while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
-    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > DP_TIMEOUT_NS) return false;
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) return false;
     __nanosleep(64);
   }
   return true;
@@ -81,19 +82,25 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restric
   pdl_trigger();
   pdl_wait();
   // state[0] = epoch of the last completed call, state[1] = CTAs done in this call, state[2] = timeout flag
-  __shared__ unsigned int s_epoch;
+  __shared__ unsigned int s_epoch, s_skip;
   const int W = A.world, R = A.rank;
   if (threadIdx.x == 0) {
     const unsigned int epoch = state[0] + 1u;
+    unsigned int skip = 0;
     if (W > 1) {
       if (blockIdx.x == 0)
         for (int q = 0; q < W; ++q) st_release_sys(A.flags[q] + R, epoch);                  // my gradients are final
       for (int q = 0; q < W; ++q)
-        if (!wait_flag(A.flags[R] + q, epoch)) atomicExch(state + 2, 1u);
+        if (!wait_flag(A.flags[R] + q, epoch, A.timeout_ns)) {
+          atomicExch(state + 2, 1u);
+          skip = 1;
+        }
     }
     s_epoch = epoch;
+    s_skip = skip;
   }
   __syncthreads();
+  const int nranges = s_skip ? 0 : A.nranges;      // a peer is missing: apply nothing (the host raises at its next health check)
   const float lr_over_bc1 = dyn2[0], inv_sqrt_bc2 = dyn2[1];
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long nthreads = (long)gridDim.x * blockDim.x;
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restric
     const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
     pp = pp - lr_over_bc1 * (mm / denom);
   };
-  for (int r = 0; r < A.nranges; ++r) {
+  for (int r = 0; r < nranges; ++r) {
     const long b4 = A.beg[r] >> 2, e4 = A.end[r] >> 2;
     if (A.mc_grad != nullptr) {
       // NVSwitch path: the reduce-scatter is one multimem.ld_reduce per element, the all-gather one multimem.st: every rank
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restric
       if (W > 1) {
         for (int q = 0; q < W; ++q) st_release_sys(A.flags[q] + W + R, epoch);               // done with your memory
         for (int q = 0; q < W; ++q)
-          if (!wait_flag(A.flags[R] + W + q, epoch)) atomicExch(state + 2, 1u);
+          if (!wait_flag(A.flags[R] + W + q, epoch, A.timeout_ns)) atomicExch(state + 2, 1u);
       }
       state[1] = 0;
       state[0] = epoch;
@@ -238,6 +245,11 @@ extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* 
   A.mc_param = peers->world > 1 ? peers->mc_param : nullptr;
   if ((A.mc_grad == nullptr) != (A.mc_param == nullptr)) return fail_arg("dp_adam_step: both or neither multicast pointer");
   if (A.mc_grad && (!aligned16(A.mc_grad) || !aligned16(A.mc_param))) return fail_arg("dp_adam_step: multicast pointers must be 16-byte aligned");
+  {
+    int secs = env_int("HMVAE_DP_TIMEOUT_S", 120);
+    if (secs < 1) secs = 1;
+    A.timeout_ns = (unsigned long long)secs * 1000000000ull;
+  }
   long total = 0;
   A.nranges = nranges;
   for (int r = 0; r < nranges; ++r) {

@@ -519,6 +519,31 @@ static int adam_launch(const hmvae_adam_tensor* tensors, int n_tensors, float lr
   return 0;
 }
 
+// Optimiser clock on the DEVICE.  clock[0] = completed Adam steps t, clock[1] = scheduler iterations (StepLR position).  One
+// thread advances both and writes {lr / (1 - b1^t), 1 / sqrt(1 - b2^t)} for the step that starts now, in double precision like
+// torch.optim.Adam does on the host.  The step's CUDA graph contains this node instead of a pinned-host -> device copy, so a host
+// that queues many replays ahead can no longer overwrite the scalars of a step that has not run yet.
+__global__ void opt_clock_tick_kernel(unsigned int* __restrict__ clock, float base_lr, float gamma, int step_size, float beta1,
+                                      float beta2, float* __restrict__ dyn2) {
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned int t = clock[0] + 1u, it = clock[1];
+  double lr = (double)base_lr;
+  if (step_size > 0) lr *= pow((double)gamma, (double)(it / (unsigned int)step_size));
+  dyn2[0] = (float)(lr / (1.0 - pow((double)beta1, (double)t)));
+  dyn2[1] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));
+  clock[0] = t;
+  clock[1] = it + 1u;
+}
+
+extern "C" int hmvae_opt_clock_tick(unsigned int* clock, float base_lr, float gamma, int step_size, float beta1, float beta2,
+                                    float* dyn2, void* stream) {
+  if (!clock || !dyn2) return fail_arg("opt_clock_tick: null pointer");
+  launch_pdl(opt_clock_tick_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, clock, base_lr, gamma, step_size, beta1, beta2, dyn2);
+  return check_launch("opt_clock_tick");
+}
+
 extern "C" int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2,
                                float eps, float weight_decay, int step, float grad_scale, void* stream) {
   if (!tensors || n_tensors < 0 || step < 1) return fail_arg("adam_step: bad arguments");

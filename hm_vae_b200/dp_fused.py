@@ -169,8 +169,12 @@ class FusedDataParallelAdam:
 
         self.params = [p for p in params]
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.step_count = 0
+        self.step_count = 0            # host mirrors of the device clock {Adam steps, scheduler iterations}
+        self.sched_iters = 0
+        self.gamma, self.step_size = 1.0, 0
         self.param_groups = [dict(lr=lr)]
+        self.group = group
+        self._live = set()
         dev = self.params[0].device
         self.offsets, self.numel = arena_layout([p.numel() for p in self.params])
         self.arenas = PeerArenas(self.numel, dev, group=group, prefer=prefer)
@@ -178,7 +182,7 @@ class FusedDataParallelAdam:
         self.m = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.v = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.state = torch.zeros(4, device=dev, dtype=torch.int32)
-        self._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._clock = torch.zeros(2, dtype=torch.int32, device=dev)
         self._dyn_dev = torch.zeros(2, dtype=torch.float32, device=dev)
         # parameters move into the arena (identical values on every rank are the caller's job: broadcast first)
         with torch.no_grad():
@@ -220,11 +224,27 @@ class FusedDataParallelAdam:
         for p in self.params:
             p.grad = None
 
+    def set_schedule(self, gamma, step_size):
+        """StepLR(step_size, gamma) evaluated on the device (hmvae_opt_clock_tick); step_size <= 0 = constant."""
+        self.gamma, self.step_size = float(gamma), int(step_size)
+
+    def current_lr(self):
+        if self.step_size > 0:
+            return self.lr * self.gamma ** (self.sched_iters // self.step_size)
+        return self.lr
+
+    def set_clock(self, step, iterations):
+        """Synchronous (checkpoint resume): Adam step count and scheduler position."""
+        self.step_count, self.sched_iters = int(step), int(iterations)
+        self._clock.copy_(torch.tensor([self.step_count, self.sched_iters], dtype=torch.int32))
+        self.param_groups[0]["lr"] = self.current_lr()
+
     def advance(self, lr=None):
+        """Host side of one step: only the mirrors move -- the step counter and the schedule position live on the device and
+        tick inside the (possibly replayed) step, so a host that runs ahead cannot change the scalars of a queued step."""
+        self.param_groups[0]["lr"] = self.current_lr()
         self.step_count += 1
-        lr = self.param_groups[0]["lr"] if lr is None else lr
-        self._dyn_host[0] = lr / (1.0 - self.betas[0] ** self.step_count)
-        self._dyn_host[1] = 1.0 / (1.0 - self.betas[1] ** self.step_count) ** 0.5
+        self.sched_iters += 1
 
     def _live_ranges(self, select):
         """Live = parameters (with index in ``select``) that received a gradient this step.  Gradients that autograd did not
@@ -238,6 +258,7 @@ class FusedDataParallelAdam:
             if p.grad.data_ptr() != self.arenas.grad.data_ptr() + 4 * off:
                 self.arenas.grad[off:off + n].view(p.shape).copy_(p.grad)
             key.append(i)
+            self._live.add(i)
             live.append((off, off + (n + ALIGN - 1) // ALIGN * ALIGN))
         key = tuple(key)
         if key not in self._range_cache:
@@ -262,8 +283,12 @@ class FusedDataParallelAdam:
                                                scale, self.state.data_ptr(), int(max_ctas), ops.stream()), "dp_adam_step")
 
     def begin_step(self):
-        """Start of a device step (capturable): the step-dependent scalars go to the device; nothing has been stepped yet."""
-        self._dyn_dev.copy_(self._dyn_host, non_blocking=True)
+        """Start of a device step (capturable): the device clock ticks and refreshes the step-dependent scalars; nothing has
+        been stepped yet."""
+        from . import ops
+
+        _lib.check(_lib.lib.hmvae_opt_clock_tick(self._clock.data_ptr(), self.lr, self.gamma, self.step_size, self.betas[0],
+                                                 self.betas[1], _lib.ptr(self._dyn_dev), ops.stream()), "opt_clock_tick")
         self._stepped = set()
         self._begun = True
 
@@ -305,29 +330,47 @@ class FusedDataParallelAdam:
         self.step_dyn(grad_scale)
 
     def timed_out(self):
-        """True if a flag barrier ever timed out (a peer died): results are invalid."""
+        """True if a flag barrier ever timed out (a peer died or fell > HMVAE_DP_TIMEOUT_S behind): the kernel then SKIPPED its
+        update (parameters stay consistent but stale).  Synchronises with the device."""
         return bool(int(self.state[2].item()))
+
+    def check_health(self):
+        if self.timed_out():
+            raise _lib.HmvaeError("fused data-parallel step: a peer did not reach the gradient barrier within HMVAE_DP_TIMEOUT_S; "
+                                  "the update was skipped on this rank -- the ranks are out of step, abort the job")
 
     # ---- checkpoints: every rank only maintains the moments of its static share of the arena
     def _full_moments(self):
+        """COLLECTIVE over ``self.group`` when world > 1: every rank must call it."""
         lo, hi = rank_share(self.numel, self.rank, self.world)
         m, v = torch.zeros_like(self.m), torch.zeros_like(self.v)
         m[lo:hi] = self.m[lo:hi]
         v[lo:hi] = self.v[lo:hi]
         if self.world > 1:
-            dist.all_reduce(m)
-            dist.all_reduce(v)
+            dist.all_reduce(m, group=self.group)
+            dist.all_reduce(v, group=self.group)
         return m, v
 
     def state_dict(self):
+        """torch.optim.Adam.state_dict() layout (the reference's optimizer.pt).  COLLECTIVE when world > 1 (the moments are
+        sharded): every rank must call it; all ranks get the full dict."""
+        from .optim_state import to_torch_adam
+
         m, v = self._full_moments()
-        return dict(step=self.step_count, lr=self.param_groups[0]["lr"],
-                    exp_avg=[m[o:o + p.numel()].view(p.shape).clone() for p, o in zip(self.params, self.offsets)],
-                    exp_avg_sq=[v[o:o + p.numel()].view(p.shape).clone() for p, o in zip(self.params, self.offsets)])
+        return to_torch_adam(self.step_count, self.current_lr(), self.betas, self.eps, self.weight_decay,
+                             [m[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)],
+                             [v[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)],
+                             live=self._live, initial_lr=self.lr)
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.param_groups[0]["lr"] = sd.get("lr", self.lr)
-        for p, o, a, b in zip(self.params, self.offsets, sd["exp_avg"], sd["exp_avg_sq"]):
-            self.m[o:o + p.numel()].copy_(a.reshape(-1))
-            self.v[o:o + p.numel()].copy_(b.reshape(-1))
+        from .optim_state import from_torch_adam
+
+        step, lr, ms, vs, live = from_torch_adam(sd, len(self.params))
+        self.m.zero_()
+        self.v.zero_()
+        for p, o, a, b in zip(self.params, self.offsets, ms, vs):
+            if a is not None:
+                self.m[o:o + p.numel()].copy_(a.reshape(-1))
+                self.v[o:o + p.numel()].copy_(b.reshape(-1))
+        self._live = set(live)
+        self.set_clock(step, self.sched_iters)

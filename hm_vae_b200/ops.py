@@ -643,15 +643,38 @@ def traj_fwdbwd(root_v_pred, root_v_gt, mean3, std3, joints, w_v, w_trans, losse
 
 
 class FusedAdam:
-    """torch.optim.Adam(lr, betas, eps, weight_decay) semantics in one multi-tensor kernel (trainer_motion_vae.py:29-31)."""
+    """torch.optim.Adam(lr, betas, eps, weight_decay) semantics in one multi-tensor kernel (trainer_motion_vae.py:29-31), with
+    torch.optim.lr_scheduler.StepLR folded in (``set_schedule``).  The step counter and the schedule position live on the device
+    (``hmvae_opt_clock_tick``): a replayed CUDA graph of the step keeps its own time."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.params = [p for p in params]
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.step_count = 0
+        self.step_count = 0            # host mirror of clock[0] (advance() is called once per step)
+        self.sched_iters = 0           # host mirror of clock[1]
+        self.gamma, self.step_size = 1.0, 0
         self.exp_avg = [torch.zeros_like(p) for p in self.params]
         self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
         self.param_groups = [dict(lr=lr)]
+        self._live = set()
+        dev = self.params[0].device
+        self._clock = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._dyn_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+
+    def set_schedule(self, gamma, step_size):
+        """StepLR(step_size, gamma) evaluated on the device; step_size <= 0 = constant learning rate."""
+        self.gamma, self.step_size = float(gamma), int(step_size)
+
+    def current_lr(self):
+        if self.step_size > 0:
+            return self.lr * self.gamma ** (self.sched_iters // self.step_size)
+        return self.lr
+
+    def set_clock(self, step, iterations):
+        """Synchronous (checkpoint resume): Adam step count and scheduler position."""
+        self.step_count, self.sched_iters = int(step), int(iterations)
+        self._clock.copy_(torch.tensor([self.step_count, self.sched_iters], dtype=torch.int32))
+        self.param_groups[0]["lr"] = self.current_lr()
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -661,11 +684,12 @@ class FusedAdam:
                 p.grad.zero_()
 
     def _pack(self):
-        live = [(p, m, v) for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq) if p.grad is not None]
+        live = [(i, p, m, v) for i, (p, m, v) in enumerate(zip(self.params, self.exp_avg, self.exp_avg_sq)) if p.grad is not None]
         arr = (_lib.AdamTensor * len(live))()
-        for i, (p, m, v) in enumerate(live):
+        for k, (i, p, m, v) in enumerate(live):
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            arr[i] = _lib.AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
+            arr[k] = _lib.AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
+            self._live.add(i)
         return arr, len(live)
 
     def _bump_versions(self):
@@ -675,44 +699,49 @@ class FusedAdam:
                 torch.autograd.graph.increment_version(p)
 
     def step(self, grad_scale=1.0, lr=None, step=None):
+        """Eager step with host-side scalars (tests / simple loops)."""
         self.step_count = self.step_count + 1 if step is None else step
+        self.sched_iters += 1
         arr, n = self._pack()
         self._bump_versions()
         check(lib.hmvae_adam_step(arr, n, self.param_groups[0]["lr"] if lr is None else lr, self.betas[0], self.betas[1],
                                   self.eps, self.weight_decay, self.step_count, grad_scale, stream()), "adam_step")
+        self._clock.copy_(torch.tensor([self.step_count, self.sched_iters], dtype=torch.int32))
 
-    # ---- CUDA-graph friendly variant: step-dependent scalars travel through a pinned host -> device copy
-    def dyn_buffers(self, device):
-        if not hasattr(self, "_dyn_host"):
-            self._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-            self._dyn_dev = torch.zeros(2, dtype=torch.float32, device=device)
-        return self._dyn_host, self._dyn_dev
-
+    # ---- CUDA-graph friendly variant: the step-dependent scalars are produced on the device
     def advance(self, lr=None):
-        """Host side of one step: bumps t and refreshes {lr/(1-b1^t), 1/sqrt(1-b2^t)} in the pinned buffer."""
+        """Host side of one step: only the mirrors move (the device clock ticks inside the step)."""
+        self.param_groups[0]["lr"] = self.current_lr()
         self.step_count += 1
-        lr = self.param_groups[0]["lr"] if lr is None else lr
-        host, _ = self.dyn_buffers(self.params[0].device)
-        host[0] = lr / (1.0 - self.betas[0] ** self.step_count)
-        host[1] = 1.0 / (1.0 - self.betas[1] ** self.step_count) ** 0.5
+        self.sched_iters += 1
+
+    def tick(self):
+        """Device side (capturable): advance the clock and refresh {lr/(1-b1^t), 1/sqrt(1-b2^t)}."""
+        check(lib.hmvae_opt_clock_tick(self._clock.data_ptr(), self.lr, self.gamma, self.step_size, self.betas[0], self.betas[1],
+                                       ptr(self._dyn_dev), stream()), "opt_clock_tick")
 
     def step_dyn(self, grad_scale=1.0):
-        """Device side (capturable): H2D copy of the two scalars + the multi-tensor kernel.  Call advance() first."""
-        host, dev = self.dyn_buffers(self.params[0].device)
-        dev.copy_(host, non_blocking=True)
+        """Device side (capturable): clock tick + the multi-tensor kernel.  Call advance() first."""
+        self.tick()
         arr, n = self._pack()
         self._bump_versions()
-        check(lib.hmvae_adam_step_dyn(arr, n, ptr(dev), self.betas[0], self.betas[1], self.eps, self.weight_decay, grad_scale,
+        check(lib.hmvae_adam_step_dyn(arr, n, ptr(self._dyn_dev), self.betas[0], self.betas[1], self.eps, self.weight_decay, grad_scale,
                                       stream()), "adam_step_dyn")
 
     def state_dict(self):
-        return dict(step=self.step_count, lr=self.param_groups[0]["lr"], exp_avg=[m.clone() for m in self.exp_avg],
-                    exp_avg_sq=[v.clone() for v in self.exp_avg_sq])
+        """torch.optim.Adam.state_dict() layout (the reference's optimizer.pt, trainer_motion_vae.py:112-113)."""
+        from .optim_state import to_torch_adam
+
+        return to_torch_adam(self.step_count, self.current_lr(), self.betas, self.eps, self.weight_decay, self.exp_avg,
+                             self.exp_avg_sq, live=self._live, initial_lr=self.lr)
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.param_groups[0]["lr"] = sd.get("lr", self.lr)
-        for m, s in zip(self.exp_avg, sd["exp_avg"]):
-            m.copy_(s)
-        for v, s in zip(self.exp_avg_sq, sd["exp_avg_sq"]):
-            v.copy_(s)
+        from .optim_state import from_torch_adam
+
+        step, lr, m, v, live = from_torch_adam(sd, len(self.params))
+        for dst, src in zip(self.exp_avg, m):
+            dst.zero_() if src is None else dst.copy_(src)
+        for dst, src in zip(self.exp_avg_sq, v):
+            dst.zero_() if src is None else dst.copy_(src)
+        self._live = set(live)
+        self.set_clock(step, self.sched_iters)

@@ -110,6 +110,7 @@ class Trainer(nn.Module):
                     from .dp_fused import FusedDataParallelAdam
                     self.gen_opt = FusedDataParallelAdam(params, lr=self.base_lr, weight_decay=self.cfg['weight_decay'],
                                                          prefer=os.environ.get("HMVAE_DP_PEER", "symm"))
+                    self._configure_schedule()
                     self._sync = _NoCollective(world)
                     self.dp_mode = "fused_peer_memory(%s)" % self.gen_opt.arenas.backend
                     # The decoder's share of the optimiser step starts as soon as the decoder's gradients are final and runs under
@@ -128,8 +129,15 @@ class Trainer(nn.Module):
                         raise
                     print("hm_vae_b200: %s -- falling back to the NCCL all-reduce path" % exc, file=sys.stderr)
             self.gen_opt = ops.FusedAdam(params, lr=self.base_lr, weight_decay=self.cfg['weight_decay'])
+            self._configure_schedule()
             self._sync = BucketedAllReduce(self.model, n_buckets=self._n_buckets)
             self.dp_mode = "nccl_bucketed_allreduce" if world > 1 else "single"
+
+    def _configure_schedule(self):
+        """StepLR (trainer_motion_vae.py:251-262) is evaluated on the device from the optimiser's own iteration counter: like
+        the reference's scheduler.step(), it advances once per gen_update call."""
+        if self.cfg.get('lr_policy', 'constant') == 'step':
+            self.gen_opt.set_schedule(self.cfg['gamma'], self.cfg['step_size'])
 
     def lr_at(self, iterations):
         """StepLR(step_size, gamma) (trainer_motion_vae.py:251-262); 'constant' when no policy is configured."""
@@ -166,7 +174,15 @@ class Trainer(nn.Module):
         if not self.sync_losses:
             return tuple(sc(v) for v in out[:9])
         vals = torch.stack([sc(v) for v in out[:9]]).tolist()      # ONE device->host sync
+        self._check_health()
         return tuple(vals)
+
+    def _check_health(self):
+        """Raises if the fused data-parallel kernel ever gave up waiting for a peer (needs a host sync: called where the host
+        synchronises anyway, in save(), and every 500 steps otherwise)."""
+        chk = getattr(self.gen_opt, "check_health", None)
+        if chk is not None:
+            chk()
 
     def gen_update(self, data, hp, iterations, multigpus=False, validation_flag=False):
         self._ensure_opt()
@@ -175,7 +191,10 @@ class Trainer(nn.Module):
                 out = self.model(data, hp, iterations, validation_flag=True)
             return self._record(out, True)
         key = self._graph_key(hp, iterations, data)
-        self.gen_opt.advance(lr=self.lr_at(iterations))
+        self._steps = getattr(self, "_steps", 0) + 1
+        if not self.sync_losses and self._steps % 500 == 0:
+            self._check_health()
+        self.gen_opt.advance()
         if key in self._graphs:
             graph, static_in, static_out = self._graphs[key]
             self._load_inputs(static_in, data)
@@ -241,7 +260,7 @@ class Trainer(nn.Module):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.gen_opt.advance(lr=self.lr_at(iterations))
+                self.gen_opt.advance()
                 self._device_step(static_in, hp, iterations)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -264,11 +283,21 @@ class Trainer(nn.Module):
 
     # ------------------------------------------------------------------ checkpoints (reference layout)
     def save(self, snapshot_dir, iterations, multigpus=False):
+        """Reference file names and dict layouts (trainer_motion_vae.py:108-113): gen_%08d.pt = {'state_dict': model.state_dict()},
+        optimizer.pt = {'gen': torch.optim.Adam-format state_dict}.  With world > 1 this is COLLECTIVE: every rank must call it
+        (the Adam moments are sharded across ranks); only rank 0 writes, and all ranks leave together."""
         self._ensure_opt()
-        gen_name = os.path.join(snapshot_dir, 'gen_%08d.pt' % (iterations + 1))
-        opt_name = os.path.join(snapshot_dir, 'optimizer.pt')
-        torch.save({'state_dict': self.model.state_dict()}, gen_name, _use_new_zipfile_serialization=False)
-        torch.save({'gen': self.gen_opt.state_dict()}, opt_name, _use_new_zipfile_serialization=False)
+        self._check_health()
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        opt_state = self.gen_opt.state_dict()             # gathers the sharded moments (collective)
+        if rank == 0:
+            gen_name = os.path.join(snapshot_dir, 'gen_%08d.pt' % (iterations + 1))
+            opt_name = os.path.join(snapshot_dir, 'optimizer.pt')
+            torch.save({'state_dict': self.model.state_dict()}, gen_name, _use_new_zipfile_serialization=False)
+            torch.save({'gen': opt_state}, opt_name, _use_new_zipfile_serialization=False)
+        if world > 1:
+            dist.barrier()
 
     def resume(self, checkpoint_dir, hp, multigpus=False):
         self._ensure_opt()
@@ -277,6 +306,8 @@ class Trainer(nn.Module):
         iterations = int(last_model_name[-11:-3])
         state = torch.load(os.path.join(checkpoint_dir, 'optimizer.pt'), weights_only=False)
         self.gen_opt.load_state_dict(state['gen'])
+        # the reference re-creates StepLR with last_epoch = iterations (trainer_motion_vae.py:126): same schedule position here
+        self.gen_opt.set_clock(self.gen_opt.step_count, iterations)
         print('Resume from iteration %d' % iterations)
         return iterations
 

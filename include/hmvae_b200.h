@@ -207,6 +207,14 @@ int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, f
 int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const float* dyn2, float beta1, float beta2,
                         float eps, float weight_decay, float grad_scale, void* stream);
 
+/* The step-dependent scalars produced ON THE DEVICE (replaces torch.optim.Adam's host-side bias corrections and
+ * torch.optim.lr_scheduler.StepLR, trainer_motion_vae.py:29-33, 251-262): clock = device uint32[2] {completed Adam steps t,
+ * scheduler iterations}; one call advances both and writes dyn2 = {lr_t / (1 - b1^t), 1 / sqrt(1 - b2^t)} with
+ * lr_t = base_lr * gamma^(iterations / step_size) (step_size <= 0: constant).  Capturable: a replayed CUDA graph of the step
+ * keeps its own time, whatever the host has queued ahead. */
+int hmvae_opt_clock_tick(unsigned int* clock, float base_lr, float gamma, int step_size, float beta1, float beta2,
+                         float* dyn2, void* stream);
+
 /* ------------------------------------------------------------------ batch assembly (utils_motion_vae.py, the step before the path)
  *
  * rand_rotation_matrix (:17-57): randnums [n,3] float64 in [0,1] -> rot [n,9] float32 (row-major), computed in float64. */

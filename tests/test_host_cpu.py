@@ -117,3 +117,45 @@ def test_cpu_tensor_is_an_error_not_a_fallback():
         fk(torch.zeros(2, 24, 3, 3))
     with pytest.raises(Exception):
         H.rotation_matrix_from_ortho6d(torch.zeros(2, 6))
+
+
+def test_optimizer_state_is_torch_adam_format_round_trip():
+    """optimizer.pt of the reference is torch.optim.Adam.state_dict() (trainer_motion_vae.py:29-31, 112-113, 121-126): the
+    converters must (a) read it, (b) write something torch.optim.Adam.load_state_dict accepts, and continuing from the
+    round-tripped state must equal an uninterrupted run."""
+    import torch
+
+    from hm_vae_b200.optim_state import from_torch_adam, to_torch_adam
+
+    gen = torch.Generator().manual_seed(0)
+    shapes = [(6, 4, 3), (6,), (5, 7), (2,)]
+    init = [torch.randn(*s, generator=gen) for s in shapes]
+    grads = [[torch.randn(*s, generator=gen) for s in shapes] for _ in range(6)]
+
+    def run(params, opt, steps):
+        for gs in steps:
+            for i, (p, g) in enumerate(zip(params, gs)):
+                p.grad = None if i == 3 else g.clone()          # parameter 3 never receives a gradient (reference D9)
+            opt.step()
+
+    pa = [torch.nn.Parameter(t.clone()) for t in init]
+    oa = torch.optim.Adam(pa, lr=1e-3, weight_decay=1e-4)
+    run(pa, oa, grads)                                          # uninterrupted
+    pb = [torch.nn.Parameter(t.clone()) for t in init]
+    ob = torch.optim.Adam(pb, lr=1e-3, weight_decay=1e-4)
+    run(pb, ob, grads[:3])
+    step, lr, m, v, live = from_torch_adam(ob.state_dict(), len(pb))          # (a) the reference's file
+    assert step == 3 and lr == 1e-3 and live == {0, 1, 2} and m[3] is None
+    ours = to_torch_adam(step, lr, (0.9, 0.999), 1e-8, 1e-4, [x if x is not None else torch.zeros(2) for x in m],
+                         [x if x is not None else torch.zeros(2) for x in v], live=live)
+    assert set(ours) == {"state", "param_groups"} and set(ours["state"]) == {0, 1, 2}
+    assert set(ours["param_groups"][0]) >= set(ob.state_dict()["param_groups"][0])
+    pc = [torch.nn.Parameter(p.detach().clone()) for p in pb]
+    oc = torch.optim.Adam(pc, lr=1e-3, weight_decay=1e-4)
+    oc.load_state_dict(ours)                                    # (b)
+    run(pc, oc, grads[3:])
+    for a, c in zip(pa, pc):
+        assert torch.equal(a, c)
+    # round-1 layout of this package is still readable
+    old = dict(step=3, lr=1e-3, exp_avg=[torch.zeros(*s) for s in shapes], exp_avg_sq=[torch.zeros(*s) for s in shapes])
+    assert from_torch_adam(old, 4)[0] == 3
