@@ -26,26 +26,36 @@ rot = ops.rot6d_to_rotmat(x6)
 data = (torch.stack((rot[..., 0], rot[..., 1]), dim=-2).reshape(bs, T, -1).contiguous(), rot.reshape(bs, T, -1).contiguous())
 if hp["model_name"] == "TrajectoryModel":
     data = (data[0], data[1], None, torch.randn(bs, T, 72, generator=g).to(dev), None, None, torch.randn(bs, T, 3, generator=g).to(dev))
-out = {}
+out, all_losses, start = {}, {}, None
 for fused in (False, True):
     torch.manual_seed(0)
     tr = Trainer(dict(hp), device=dev, sync_losses=False, dp_fused=fused).to(dev)
     ddp.broadcast_parameters(tr.model)
+    if start is None:
+        start = {k: v.detach().clone() for k, v in tr.model.named_parameters()}
     torch.manual_seed(50 + rank)
     losses = [float(tr.gen_update(data, hp, 0)[0]) for _ in range(3)]
     torch.cuda.synchronize()
+    all_losses[fused] = losses
     out[fused] = {k: v.detach().clone() for k, v in tr.model.named_parameters()}
     if fused:
         print("rank %d: dp_mode %s timed_out %s losses %s" % (rank, tr.dp_mode, tr.gen_opt.timed_out(), losses), flush=True)
     else:
         print("rank %d: dp_mode %s losses %s" % (rank, tr.dp_mode, losses), flush=True)
     ops.unregister_grad_buffers()
-# Adam's first updates are ~ +-lr whatever the gradient's magnitude, so an element whose gradient is rounding noise can move in
-# opposite directions under two different summation orders (fixed rank order here, ring / tree in NCCL): bound = 2 * lr * steps.
+# What is compared, and why the parameter bound is loose HERE (the tight, kernel-level proof is tools/dp_kernel_check.py):
+# the two runs use two different Adam kernels (dp_adam_kernel vs the multi-tensor adam_kernel) whose results differ in the last
+# bit (FMA contraction), so from step 2 on their losses / gradients differ at the 1e-7 level.  Adam's early updates are ~ +-lr
+# whatever the gradient's magnitude, so the ~1 % of elements whose gradient is itself rounding noise (|g| ~ 1e-9, e.g. weights
+# of taps that only ever see the reflect padding) can move in opposite directions: |dp| <= 2 * lr * steps for those.  Losses must
+# agree to 1e-5, every rank must hold bit-identical parameters, and the update as a whole must agree to 5 % relative-L2.
 worst, differing, total = 0.0, 0, 0
+num = den = 0.0
 for k in out[False]:
     a, b = out[True][k].double(), out[False][k].double()
     d = (a - b).abs()
+    num += float(((a - b) ** 2).sum())
+    den += float(((b - start[k].double()) ** 2).sum())
     worst = max(worst, float(d.max()))
     differing += int((d > 1e-6).sum())
     total += d.numel()
@@ -54,8 +64,11 @@ chk = torch.stack([v.double().sum() for v in out[True].values()]).sum().reshape(
 gathered = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(gathered, chk)
 same = all(float(t) == float(gathered[0]) for t in gathered)
-print("rank %d: fused vs nccl worst abs parameter diff %.3e (bound 2*lr*steps = 6e-4), %.4f%% of elements differ by > 1e-6; "
-      "ranks identical: %s" % (rank, worst, 100.0 * differing / total, same), flush=True)
+upd_rel = (num / max(den, 1e-300)) ** 0.5
+loss_rel = max(abs(a - b) / abs(b) for a, b in zip(all_losses[True], all_losses[False]))
+print("rank %d: fused vs nccl: losses agree to %.2e; update relative-L2 difference %.3e; worst abs parameter diff %.3e (bound "
+      "2*lr*steps = 6e-4), %.4f%% of elements differ by > 1e-6; ranks identical: %s" % (
+          rank, loss_rel, upd_rel, worst, 100.0 * differing / total, same), flush=True)
 dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if (worst <= 6.5e-4 and differing <= 0.05 * total and same) else 1)
+sys.exit(0 if (loss_rel <= 1e-5 and upd_rel <= 0.05 and worst <= 6.5e-4 and differing <= 0.05 * total and same) else 1)

@@ -1,0 +1,107 @@
+"""Multi-rank parity of hmvae_dp_adam_step (csrc/dp.cu) at the KERNEL level, run under torchrun with >= 2 GPUs:
+
+    torchrun --nproc-per-node W tools/dp_kernel_check.py            # HMVAE_DP_MULTICAST=0 / 1 selects unicast / NVLS
+
+Every rank writes its own seeded N(0,1) gradients into its gradient arena (the way the weight-gradient kernels do), then 3 fused
+reduce-scatter + Adam + all-gather steps run.  The reference is computed independently on every rank from the NCCL all-gathered
+gradients: G = ((g_0 + g_1) + ...) * (1/W) in fp32, then torch.optim.Adam.  With O(1) gradients there is no "Adam sign noise"
+(an update is +-lr whatever the magnitude of a rounding-level gradient), so the bounds are tight:
+    reduced gradient before Adam (recovered from exp_avg after step 1: m_1 = (1-b1) * (G + wd*p))   <= 1e-6 relative-L2
+    exp_avg / exp_avg_sq after 3 steps                                                              <= 1e-5 relative-L2
+    parameters after 3 steps                                                                        <= 2e-7 absolute
+    all ranks hold bit-identical parameters.
+Exit code 0 = pass.  tests/test_dp_multi_gpu.py spawns this when >= 2 GPUs are visible."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from hm_vae_b200 import ddp, ops  # noqa: E402
+from hm_vae_b200.dp_fused import FusedDataParallelAdam  # noqa: E402
+
+rank, world, local = ddp.init_from_env("nccl")
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+LR, WD, B1, B2 = 1e-4, 1e-4, 0.9, 0.999
+shapes = [(288, 144, 15), (288,), (24, 384), (3,), (7,), (672, 336, 15), (336,)]
+DEAD = 2                                   # never receives a gradient: must stay untouched (torch skips grad=None)
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+gen = torch.Generator().manual_seed(7)
+init = [torch.randn(*s, generator=gen) for s in shapes]
+mine = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
+opt = FusedDataParallelAdam(mine, lr=LR, weight_decay=WD)
+ref_p = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
+ref = torch.optim.Adam(ref_p, lr=LR, betas=(B1, B2), weight_decay=WD)
+fails = []
+for step in range(1, 4):
+    g = torch.Generator().manual_seed(1000 * step + rank)
+    grads = [torch.randn(*s, generator=g).to(dev) for s in shapes]
+    for i, (p, gr) in enumerate(zip(mine, grads)):
+        if i == DEAD:
+            p.grad = None
+            continue
+        buf = ops.grad_buffer(p)
+        buf.copy_(gr)
+        p.grad = buf
+    # reference: all-gather over NCCL, fixed-order fp32 sum, mean
+    for i, (p, gr) in enumerate(zip(ref_p, grads)):
+        if i == DEAD:
+            p.grad = None
+            continue
+        parts = [torch.empty_like(gr) for _ in range(world)]
+        dist.all_gather(parts, gr)
+        G = parts[0].clone()
+        for q in range(1, world):
+            G = G + parts[q]
+        p.grad = G * (1.0 / world)
+    if step == 1:
+        expect_gg = [None if p.grad is None else (p.grad + WD * p.detach()) for p in ref_p]
+    opt.step()
+    ref.step()
+    torch.cuda.synchronize()
+    if step == 1:
+        sd = opt.state_dict()                       # collective: full exp_avg on every rank
+        for i in range(len(shapes)):
+            if i == DEAD:
+                continue
+            got = sd["state"][i]["exp_avg"] / (1.0 - B1)
+            e = rel_l2(got, expect_gg[i])
+            if e > 1e-6:
+                fails.append("step 1 reduced gradient of tensor %d: rel-L2 %.3e" % (i, e))
+sd = opt.state_dict()
+worst_p = 0.0
+for i, (a, b) in enumerate(zip(mine, ref_p)):
+    d = float((a.detach() - b.detach()).abs().max())
+    worst_p = max(worst_p, d)
+    if i == DEAD:
+        if d != 0.0:
+            fails.append("dead parameter moved")
+        continue
+    em, ev = rel_l2(sd["state"][i]["exp_avg"], ref.state[b]["exp_avg"]), rel_l2(sd["state"][i]["exp_avg_sq"], ref.state[b]["exp_avg_sq"])
+    if em > 1e-5 or ev > 1e-5:
+        fails.append("tensor %d: exp_avg rel-L2 %.3e, exp_avg_sq rel-L2 %.3e" % (i, em, ev))
+    if d > 2e-7:
+        fails.append("tensor %d: parameter max abs diff %.3e" % (i, d))
+if DEAD in sd["state"]:
+    fails.append("dead parameter has optimiser state")
+chk = torch.stack([p.detach().double().sum() for p in mine]).sum().reshape(1)
+gathered = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(gathered, chk)
+same = all(float(t) == float(gathered[0]) for t in gathered)
+if not same:
+    fails.append("ranks hold different parameters")
+if opt.timed_out():
+    fails.append("flag barrier timed out")
+print("rank %d/%d: backend %s, worst parameter abs diff %.3e, ranks identical %s, %s" % (
+    rank, world, opt.arenas.backend, worst_p, same, "PASS" if not fails else "FAIL: " + "; ".join(fails)), flush=True)
+opt.close()
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(1 if fails else 0)
