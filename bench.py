@@ -240,6 +240,35 @@ def other_configs_leg(dev):
             del tr
         except Exception as exc:        # reported, never fatal for the headline line
             out[tag] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    # the latent-space optimisation loop of configs/len_64_test_interpolation.yaml (150 iterations: 51 on the
+    # latents, 99 on the decoder copy; one window, bs = 1 as in the reference), two CUDA graphs, losses kept on the device
+    try:
+        from hm_vae_b200.seq_two_hier_sa_vae import TwoHierSAVAEModel
+
+        hp = load_cfg("len_64_test_interpolation.yaml")
+        torch.manual_seed(0)
+        model = TwoHierSAVAEModel(dict(hp), device=dev).to(dev)
+        d6, dm = synthetic_device_batch(1, hp["train_seq_len"], dev, 1234)
+        T = hp["train_seq_len"]
+        mask = torch.zeros(1, T, 24, device=dev)
+        mask[:, ::hp["interpolation_window"]] = 1
+        mask[:, -1] = 1
+        model.optimize_latent(d6.view(1, T, 24, 6), dm.view(1, T, 24, 3, 3), mask, hp)          # warm-up (plans, allocator)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        res = model.optimize_latent(d6.view(1, T, 24, 6), dm.view(1, T, 24, 3, 3), mask, hp)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        hist = res["losses"].cpu()
+        out["latent_optimisation"] = {"config": "configs/len_64_test_interpolation.yaml", "batch": 1, "iterations": int(hp["opt_it"]),
+                                      "ms_total": ms, "ms_per_iteration": ms / hp["opt_it"], "loss_first": float(hist[0, 5]),
+                                      "loss_last": float(hist[-1, 5]), "cuda_graph": True,
+                                      "note": "includes graph capture of both phases (2 eager + 2 capture iterations)"}
+        del model
+    except Exception as exc:
+        out["latent_optimisation"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     return out
 
 

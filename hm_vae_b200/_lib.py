@@ -5,7 +5,7 @@ PyTorch/CPU fallback anywhere in the package.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_longlong, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_long, c_longlong, c_void_p
 
 import torch
 
@@ -64,6 +64,10 @@ class AdamTensor(Structure):
     _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("numel", c_long)]
 
 
+class RegTensor(Structure):
+    _fields_ = [("p", c_void_p), ("p0", c_void_p), ("g", c_void_p), ("numel", c_long), ("accumulate", c_int)]
+
+
 DP_MAX_WORLD, DP_MAX_RANGES = 8, 64
 
 
@@ -110,18 +114,20 @@ _SIGS = {
     "hmvae_latent_fwd": (c_int, [P, P, P, P, c_long, c_int, P]),
     "hmvae_latent_bwd": (c_int, [P, P, P, P, P, c_long, c_int, c_float, P]),
     "hmvae_recon_fwdbwd": (c_int, [P, c_int, P, P, P, IP, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P]),
+    "hmvae_recon_masked_fwdbwd": (c_int, [P, c_int, P, P, P, P, IP, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P, P]),
+    "hmvae_l2_reg_fwdbwd": (c_int, [POINTER(RegTensor), c_int, c_float, P, P]),
     "hmvae_linear_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_linear_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_loss_finalize": (c_int, [P, P, POINTER(c_float), POINTER(c_float), POINTER(c_float), c_int, P]),
     "hmvae_mse_fwd": (c_int, [P, P, P, c_long, P]),
     "hmvae_mse_bwd": (c_int, [P, P, P, c_long, c_float, P]),
     "hmvae_traj_fwdbwd": (c_int, [P, P, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, c_float, c_float, P, P, P]),
-    "hmvae_adam_step": (c_int, [POINTER(AdamTensor), c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
-    "hmvae_adam_step_dyn": (c_int, [POINTER(AdamTensor), c_int, P, c_float, c_float, c_float, c_float, c_float, P]),
-    "hmvae_opt_clock_tick": (c_int, [P, c_float, c_float, c_int, c_float, c_float, P, P]),
+    "hmvae_adam_step": (c_int, [POINTER(AdamTensor), c_int, c_float, c_double, c_double, c_float, c_float, c_int, c_float, P]),
+    "hmvae_adam_step_dyn": (c_int, [POINTER(AdamTensor), c_int, P, c_double, c_double, c_float, c_float, c_float, P]),
+    "hmvae_opt_clock_tick": (c_int, [P, c_float, c_float, c_int, c_double, c_double, P, P]),
     "hmvae_rand_rotation": (c_int, [P, ctypes.c_double, P, c_long, P]),
     "hmvae_batch_assemble": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
-    "hmvae_dp_adam_step": (c_int, [POINTER(DpPeers), P, P, POINTER(c_long), c_int, P, c_float, c_float, c_float, c_float, c_float, P, c_int, P]),
+    "hmvae_dp_adam_step": (c_int, [POINTER(DpPeers), P, P, POINTER(c_long), c_int, P, c_double, c_double, c_float, c_float, c_float, P, c_int, P]),
     "hmvae_ipc_alloc": (c_int, [c_long, POINTER(c_void_p)]),
     "hmvae_ipc_free": (c_int, [c_void_p]),
     "hmvae_ipc_get_handle": (c_int, [c_void_p, P]),

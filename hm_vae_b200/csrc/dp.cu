@@ -77,7 +77,7 @@ __device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int
 
 template <bool TWO>      // TWO: two float4 per thread and iteration (multi-rank: more peer loads in flight; costs registers)
 __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restrict__ m, float* __restrict__ v,
-                                                      const float* __restrict__ dyn2, float beta1, float beta2, float eps,
+                                                      const float* __restrict__ dyn2, float omb1, float beta2, float omb2, float eps,
                                                       float wd, float gscale, unsigned int* __restrict__ state) {
   pdl_trigger();
   pdl_wait();
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restric
   const long nthreads = (long)gridDim.x * blockDim.x;
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     gg = gg * gscale + wd * pp;
-    mm = mm + (gg - mm) * (1.f - beta1);
-    vv = vv * beta2 + (1.f - beta2) * gg * gg;
+    mm = mm + (gg - mm) * omb1;
+    vv = vv * beta2 + omb2 * gg * gg;
     const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
     pp = pp - lr_over_bc1 * (mm / denom);
   };
@@ -223,12 +223,13 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restric
 using namespace hmvae;
 
 extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges,
-                                  const float* dyn2, float beta1, float beta2, float eps, float weight_decay,
+                                  const float* dyn2, double beta1, double beta2, float eps, float weight_decay,
                                   float grad_scale, unsigned int* state, int max_ctas, void* stream) {
   if (!peers || !m || !v || !dyn2 || !state || (nranges > 0 && !ranges)) return fail_arg("dp_adam_step: null pointer");
   if (peers->world < 1 || peers->world > HMVAE_DP_MAX_WORLD || peers->rank < 0 || peers->rank >= peers->world)
     return fail_arg("dp_adam_step: bad world / rank");
   if (nranges < 0 || nranges > HMVAE_DP_MAX_RANGES) return fail_arg("dp_adam_step: too many ranges");
+  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);      // 1 - beta rounded ONCE from double, like torch
   DpArgs A;
   A.world = peers->world;
   A.rank = peers->rank;
@@ -265,9 +266,9 @@ extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* 
   if (max_ctas > 0 && blocks > max_ctas) blocks = max_ctas;      // a call that runs under other kernels leaves them room
   if (blocks < 1) blocks = 1;
   if (A.world > 1 && A.mc_grad == nullptr)
-    launch_pdl(dp_adam_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state);
+    launch_pdl(dp_adam_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, omb1, (float)beta2, omb2, eps, weight_decay, grad_scale, state);
   else
-    launch_pdl(dp_adam_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state);
+    launch_pdl(dp_adam_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, omb1, (float)beta2, omb2, eps, weight_decay, grad_scale, state);
   return check_launch("dp_adam_step");
 }
 

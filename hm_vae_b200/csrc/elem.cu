@@ -232,6 +232,29 @@ __global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restr
     da[o] = scale * (a[o] - b[o]);
 }
 
+// ------------------------------------------------------------------------------------------------ weight regulariser
+// Decoder-weight L2 regulariser of the latent-space optimisation loops (seq_two_hier_sa_vae.py:1382-1387, 1717-1722):
+//   l_reg = sum_i mean((p_i - p0_i)^2),   dl/dp_i = 2 (p_i - p0_i) / numel_i.
+// One launch for all tensors (blockIdx.y = tensor); the loss sum is accumulated atomically, the gradient (times `weight`) is
+// ADDED to g when `accumulate` is set for the tensor (a gradient written by the backward pass) or stored otherwise.
+constexpr int REG_MAX_T = 64;
+struct RegPack {
+  hmvae_reg_tensor t[REG_MAX_T];
+};
+__global__ void __launch_bounds__(EW_TPB) l2_reg_kernel(RegPack pack, float weight, float* __restrict__ loss) {
+  const hmvae_reg_tensor T = pack.t[blockIdx.y];
+  const float inv_n = 1.f / (float)T.numel;
+  const float gs = 2.f * weight * inv_n;
+  float acc = 0.f;
+  for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < T.numel; o += (long)gridDim.x * blockDim.x) {
+    const float d = T.p[o] - T.p0[o];
+    acc += d * d;
+    if (T.g) T.g[o] = T.accumulate ? T.g[o] + gs * d : gs * d;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * inv_n);
+}
+
 // ------------------------------------------------------------------------------------------------ trajectory
 // trajectory_pred_model.py:289-303 + :237-244.  One thread per (sequence, coordinate): forward prefix sum over T of the
 // de-standardised velocity (t >= 1), then a reverse prefix sum for the gradient.  T <= 1024.
@@ -288,8 +311,8 @@ struct AdamPack {
   hmvae_adam_tensor t[ADAM_MAX_T];
 };
 
-__global__ void __launch_bounds__(EW_TPB) adam_kernel(AdamPack pack, float lr_over_bc1, float inv_sqrt_bc2, float beta1,
-                                                      float beta2, float eps, float wd, float gscale,
+__global__ void __launch_bounds__(EW_TPB) adam_kernel(AdamPack pack, float lr_over_bc1, float inv_sqrt_bc2, float omb1,
+                                                      float beta2, float omb2, float eps, float wd, float gscale,
                                                       const float* __restrict__ dyn2) {
   pdl_trigger();
   pdl_wait();
@@ -307,8 +330,8 @@ __global__ void __launch_bounds__(EW_TPB) adam_kernel(AdamPack pack, float lr_ov
                     reinterpret_cast<uintptr_t>(v)) & 15) == 0 ? n / 4 : 0;
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     gg = gg * gscale + wd * pp;
-    mm = mm + (gg - mm) * (1.f - beta1);
-    vv = vv * beta2 + (1.f - beta2) * gg * gg;
+    mm = mm + (gg - mm) * omb1;
+    vv = vv * beta2 + omb2 * gg * gg;
     const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
     pp = pp - lr_over_bc1 * (mm / denom);
   };
@@ -494,8 +517,29 @@ extern "C" int hmvae_traj_fwdbwd(const float* root_v_pred, const float* root_v_g
   return check_launch("traj_fwdbwd");
 }
 
+extern "C" int hmvae_l2_reg_fwdbwd(const hmvae_reg_tensor* tensors, int n_tensors, float weight, float* loss, void* stream) {
+  if (n_tensors > 0 && !tensors) return fail_arg("l2_reg_fwdbwd: null pointer");
+  for (int base = 0; base < n_tensors; base += REG_MAX_T) {
+    RegPack pack;
+    const int cnt = n_tensors - base < REG_MAX_T ? n_tensors - base : REG_MAX_T;
+    long maxn = 0;
+    for (int i = 0; i < cnt; ++i) {
+      pack.t[i] = tensors[base + i];
+      if (!pack.t[i].p || !pack.t[i].p0 || pack.t[i].numel <= 0) return fail_arg("l2_reg_fwdbwd: null tensor pointer / empty tensor");
+      if (pack.t[i].numel > maxn) maxn = pack.t[i].numel;
+    }
+    long bx = (maxn + 4 * EW_TPB - 1) / (4 * EW_TPB), cap = (long)num_sms() * 2;
+    if (bx < 1) bx = 1;
+    if (bx > cap) bx = cap;
+    l2_reg_kernel<<<dim3((unsigned)bx, (unsigned)cnt), EW_TPB, 0, (cudaStream_t)stream>>>(pack, weight, loss);
+    int rc = check_launch("l2_reg_fwdbwd");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 static int adam_launch(const hmvae_adam_tensor* tensors, int n_tensors, float lr_over_bc1, float inv_sqrt_bc2,
-                       const float* dyn2, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                       const float* dyn2, double beta1, double beta2, float eps, float weight_decay, float grad_scale,
                        void* stream) {
   for (int base = 0; base < n_tensors; base += ADAM_MAX_T) {
     AdamPack pack;
@@ -512,7 +556,7 @@ static int adam_launch(const hmvae_adam_tensor* tensors, int n_tensors, float lr
     if (bx < 1) bx = 1;
     if (bx > cap) bx = cap;
     dim3 grid((unsigned)bx, (unsigned)cnt);
-    launch_pdl(adam_kernel, dim3(grid), dim3(EW_TPB), 0, (cudaStream_t)stream, pack, lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, weight_decay, grad_scale, dyn2);
+    launch_pdl(adam_kernel, dim3(grid), dim3(EW_TPB), 0, (cudaStream_t)stream, pack, lr_over_bc1, inv_sqrt_bc2, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, weight_decay, grad_scale, dyn2);
     int rc = check_launch("adam_step");
     if (rc) return rc;
   }
@@ -523,38 +567,38 @@ static int adam_launch(const hmvae_adam_tensor* tensors, int n_tensors, float lr
 // thread advances both and writes {lr / (1 - b1^t), 1 / sqrt(1 - b2^t)} for the step that starts now, in double precision like
 // torch.optim.Adam does on the host.  The step's CUDA graph contains this node instead of a pinned-host -> device copy, so a host
 // that queues many replays ahead can no longer overwrite the scalars of a step that has not run yet.
-__global__ void opt_clock_tick_kernel(unsigned int* __restrict__ clock, float base_lr, float gamma, int step_size, float beta1,
-                                      float beta2, float* __restrict__ dyn2) {
+__global__ void opt_clock_tick_kernel(unsigned int* __restrict__ clock, float base_lr, float gamma, int step_size, double beta1,
+                                      double beta2, float* __restrict__ dyn2) {
   pdl_trigger();
   pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const unsigned int t = clock[0] + 1u, it = clock[1];
   double lr = (double)base_lr;
   if (step_size > 0) lr *= pow((double)gamma, (double)(it / (unsigned int)step_size));
-  dyn2[0] = (float)(lr / (1.0 - pow((double)beta1, (double)t)));
-  dyn2[1] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));
+  dyn2[0] = (float)(lr / (1.0 - pow(beta1, (double)t)));
+  dyn2[1] = (float)(1.0 / sqrt(1.0 - pow(beta2, (double)t)));
   clock[0] = t;
   clock[1] = it + 1u;
 }
 
-extern "C" int hmvae_opt_clock_tick(unsigned int* clock, float base_lr, float gamma, int step_size, float beta1, float beta2,
+extern "C" int hmvae_opt_clock_tick(unsigned int* clock, float base_lr, float gamma, int step_size, double beta1, double beta2,
                                     float* dyn2, void* stream) {
   if (!clock || !dyn2) return fail_arg("opt_clock_tick: null pointer");
   launch_pdl(opt_clock_tick_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, clock, base_lr, gamma, step_size, beta1, beta2, dyn2);
   return check_launch("opt_clock_tick");
 }
 
-extern "C" int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2,
+extern "C" int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, double beta1, double beta2,
                                float eps, float weight_decay, int step, float grad_scale, void* stream) {
   if (!tensors || n_tensors < 0 || step < 1) return fail_arg("adam_step: bad arguments");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   return adam_launch(tensors, n_tensors, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), nullptr, beta1, beta2, eps,
                      weight_decay, grad_scale, stream);
 }
 
-extern "C" int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const float* dyn2, float beta1,
-                                   float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+extern "C" int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const float* dyn2, double beta1,
+                                   double beta2, float eps, float weight_decay, float grad_scale, void* stream) {
   if (!tensors || n_tensors < 0 || !dyn2) return fail_arg("adam_step_dyn: bad arguments");
   return adam_launch(tensors, n_tensors, 0.f, 0.f, dyn2, beta1, beta2, eps, weight_decay, grad_scale, stream);
 }

@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(32 * RC_FR) recon_par_kernel(const float* __re
                                                                const float* __restrict__ offsets, int B, int T, float s6,
                                                                float srot, float spos, float* __restrict__ losses,
                                                                float* __restrict__ dx6, float* __restrict__ pos_out,
-                                                               float* __restrict__ gtpos_out, ParTree tr) {
+                                                               float* __restrict__ gtpos_out, const float* __restrict__ mask,
+                                                               float* __restrict__ rot_out, ParTree tr) {
   pdl_trigger();
   pdl_wait();
   __shared__ float s_tile[NCW ? 6 * FK_MAX_J * RC_TP : 1];
@@ -71,6 +72,9 @@ __global__ void __launch_bounds__(32 * RC_FR) recon_par_kernel(const float* __re
 
   float a6[6], g6v[6], R[9], Rt[9], M[9], G[9];
   float l6 = 0.f, lrot = 0.f, lpos = 0.f;
+  // per (frame, joint) weight of the squared errors: l2_masked_criterion (seq_two_hier_sa_vae.py:717-735) multiplies the
+  // element-wise squared error by mask[b, t, joint] before the mean over ALL elements; no mask = plain l2_criterion
+  const float mk = (mask && act) ? mask[f * J + i] : 1.f;
 #pragma unroll
   for (int k = 0; k < 9; ++k) { R[k] = 0.f; Rt[k] = 0.f; M[k] = 0.f; G[k] = 0.f; }
 #pragma unroll
@@ -85,11 +89,12 @@ __global__ void __launch_bounds__(32 * RC_FR) recon_par_kernel(const float* __re
     for (int k = 0; k < 9; ++k) Rt[k] = gtR[f * r9 + 9 * i + k];
     rot6d_fwd(a6, R);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { const float d = a6[k] - g6v[k]; l6 += d * d; }
+    for (int k = 0; k < 6; ++k) { const float d = a6[k] - g6v[k]; l6 += mk * d * d; }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const float d = R[k] - Rt[k];
-      lrot += d * d;
+      lrot += mk * d * d;
+      if (rot_out) rot_out[f * r9 + 9 * i + k] = R[k];
       s_R[w][i][k] = R[k];
       s_Rt[w][i][k] = Rt[k];
     }
@@ -125,8 +130,8 @@ __global__ void __launch_bounds__(32 * RC_FR) recon_par_kernel(const float* __re
     for (int a = 0; a < 3; ++a) {
       const float pp = s_off[a] + v[a], pg = s_off[a] + vg[a];
       const float d = pp - pg;
-      lpos += d * d;
-      gpos[a] = spos * d;
+      lpos += mk * d * d;
+      gpos[a] = spos * mk * d;
       s_S[w][i][a] = gpos[a];
       if (pos_out) pos_out[f * r3 + 3 * i + a] = pp;
       if (gtpos_out) gtpos_out[f * r3 + 3 * i + a] = pg;
@@ -180,11 +185,11 @@ __global__ void __launch_bounds__(32 * RC_FR) recon_par_kernel(const float* __re
           for (int b = 0; b < 3; ++b) dR[a * 3 + b] = M[a] * G[b] + M[3 + a] * G[3 + b] + M[6 + a] * G[6 + b];
       }
 #pragma unroll
-      for (int k = 0; k < 9; ++k) dR[k] += srot * (R[k] - Rt[k]);
+      for (int k = 0; k < 9; ++k) dR[k] += srot * mk * (R[k] - Rt[k]);
       rot6d_bwd(a6, dR, out);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        const float o = out[k] + s6 * (a6[k] - g6v[k]);
+        const float o = out[k] + s6 * mk * (a6[k] - g6v[k]);
         if (NCW) s_tile[(6 * i + k) * RC_TP + w] = o;
         else dx6[f * r6 + 6 * i + k] = o;
       }
@@ -214,10 +219,10 @@ __global__ void __launch_bounds__(32 * RC_FR) recon_par_kernel(const float* __re
 template <bool NCW>
 static int launch_recon_par(const float* x6p, const float* gt6, const float* gtR, const float* offsets, int B, int T, float s6,
                             float srot, float spos, float* losses, float* dx6, float* pos_out, float* gtpos_out,
-                            const ParTree& tr, cudaStream_t st) {
+                            const float* mask, float* rot_out, const ParTree& tr, cudaStream_t st) {
   const long tiles = ((long)B * T + RC_FR - 1) / RC_FR;
   if (tiles > 0x7fffffffL) return fail_arg("recon_fwdbwd: too many frames");
-  launch_pdl(recon_par_kernel<NCW>, dim3((int)tiles), dim3(32 * RC_FR), 0, st, x6p, gt6, gtR, offsets, B, T, s6, srot, spos, losses, dx6, pos_out, gtpos_out, tr);
+  launch_pdl(recon_par_kernel<NCW>, dim3((int)tiles), dim3(32 * RC_FR), 0, st, x6p, gt6, gtR, offsets, B, T, s6, srot, spos, losses, dx6, pos_out, gtpos_out, mask, rot_out, tr);
   return check_launch("recon_fwdbwd");
 }
 
@@ -225,10 +230,10 @@ static int launch_recon_par(const float* x6p, const float* gt6, const float* gtR
 
 using namespace hmvae;
 
-extern "C" int hmvae_recon_fwdbwd(const float* x6_pred, int ncw, const float* gt_6d, const float* gt_rotmat,
-                                  const float* offsets, const int* parents, int joints, int batch, int t, float s6,
-                                  float srot, float spos, float* losses, float* dx6, float* pos_pred_out,
-                                  float* gt_pos_out, void* stream) {
+extern "C" int hmvae_recon_masked_fwdbwd(const float* x6_pred, int ncw, const float* gt_6d, const float* gt_rotmat,
+                                         const float* mask, const float* offsets, const int* parents, int joints, int batch,
+                                         int t, float s6, float srot, float spos, float* losses, float* dx6,
+                                         float* pos_pred_out, float* gt_pos_out, float* rot_pred_out, void* stream) {
   if (!x6_pred || !gt_6d || !gt_rotmat || !offsets || !parents || !losses) return fail_arg("recon_fwdbwd: null pointer");
   if (batch <= 0 || t <= 0) return 0;
   if (joints < 1 || joints > FK_MAX_J) return fail_arg("recon_fwdbwd: joints must be in [1, 32]");
@@ -250,6 +255,14 @@ extern "C" int hmvae_recon_fwdbwd(const float* x6_pred, int ncw, const float* gt
     tr.child_idx[tr.child_off[p] + fill[p]++] = (signed char)i;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (ncw) return launch_recon_par<true>(x6_pred, gt_6d, gt_rotmat, offsets, batch, t, s6, srot, spos, losses, dx6, pos_pred_out, gt_pos_out, tr, st);
-  return launch_recon_par<false>(x6_pred, gt_6d, gt_rotmat, offsets, batch, t, s6, srot, spos, losses, dx6, pos_pred_out, gt_pos_out, tr, st);
+  if (ncw) return launch_recon_par<true>(x6_pred, gt_6d, gt_rotmat, offsets, batch, t, s6, srot, spos, losses, dx6, pos_pred_out, gt_pos_out, mask, rot_pred_out, tr, st);
+  return launch_recon_par<false>(x6_pred, gt_6d, gt_rotmat, offsets, batch, t, s6, srot, spos, losses, dx6, pos_pred_out, gt_pos_out, mask, rot_pred_out, tr, st);
+}
+
+extern "C" int hmvae_recon_fwdbwd(const float* x6_pred, int ncw, const float* gt_6d, const float* gt_rotmat,
+                                  const float* offsets, const int* parents, int joints, int batch, int t, float s6,
+                                  float srot, float spos, float* losses, float* dx6, float* pos_pred_out,
+                                  float* gt_pos_out, void* stream) {
+  return hmvae_recon_masked_fwdbwd(x6_pred, ncw, gt_6d, gt_rotmat, nullptr, offsets, parents, joints, batch, t, s6, srot, spos,
+                                   losses, dx6, pos_pred_out, gt_pos_out, nullptr, stream);
 }

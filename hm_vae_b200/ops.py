@@ -614,9 +614,12 @@ def l2_criterion(pred, gt):
 
 
 # ------------------------------------------------------------------------------------------------ fused losses / optimiser
-def recon_fwdbwd(x6_pred, ncw, gt_6d, gt_rotmat, offsets, parents, w6d, wrot, wpos, losses, want_grad=True):
+def recon_fwdbwd(x6_pred, ncw, gt_6d, gt_rotmat, offsets, parents, w6d, wrot, wpos, losses, want_grad=True, mask=None,
+                 rot_out=None, pos_out=None):
     """Fused GT-FK + rot6d + FK + 3 MSE (+ gradient w.r.t. x6_pred).  `losses` is a zeroed float32[>=3] device tensor
-    that receives the three squared-error SUMS.  Returns dx6 (same layout as x6_pred) or None."""
+    that receives the three squared-error SUMS.  Returns dx6 (same layout as x6_pred) or None.
+    ``mask`` [B, T, joints]: l2_masked_criterion weights (seq_two_hier_sa_vae.py:717-735); ``rot_out`` [B,T,J,3,3] / ``pos_out``
+    [B,T,J,3]: optional outputs of the predicted rotation matrices / FK positions."""
     x6_pred = x6_pred.contiguous()
     if ncw:
         b, c, t = x6_pred.shape
@@ -625,10 +628,27 @@ def recon_fwdbwd(x6_pred, ncw, gt_6d, gt_rotmat, offsets, parents, w6d, wrot, wp
     j = c // 6
     nf = float(b * t)
     dx6 = torch.empty_like(x6_pred) if want_grad else None
-    check(lib.hmvae_recon_fwdbwd(ptr(x6_pred), int(ncw), ptr(_lib.aligned(gt_6d)), ptr(_lib.aligned(gt_rotmat)), ptr(offsets),
-                                 int_array(parents), j, b, t, 2.0 * w6d / (nf * 6 * j), 2.0 * wrot / (nf * 9 * j),
-                                 2.0 * wpos / (nf * 3 * j), ptr(losses), ptr(dx6), None, None, stream()), "recon_fwdbwd")
+    if mask is not None:
+        mask = mask.to(dtype=torch.float32).contiguous()
+        if mask.numel() != b * t * j:
+            raise ValueError("mask must be [B, T, joints]")
+    check(lib.hmvae_recon_masked_fwdbwd(ptr(x6_pred), int(ncw), ptr(_lib.aligned(gt_6d)), ptr(_lib.aligned(gt_rotmat)), ptr(mask),
+                                        ptr(offsets), int_array(parents), j, b, t, 2.0 * w6d / (nf * 6 * j),
+                                        2.0 * wrot / (nf * 9 * j), 2.0 * wpos / (nf * 3 * j), ptr(losses), ptr(dx6), ptr(pos_out),
+                                        None, ptr(rot_out), stream()), "recon_fwdbwd")
     return dx6
+
+
+def l2_reg_fwdbwd(params, refs, weight, loss, grads=None, accumulate=None):
+    """loss[0] += sum_i mean((p_i - ref_i)^2); grads[i] (+)= weight * 2 (p_i - ref_i) / numel_i  (one launch).
+    ``grads[i]`` may be None (value only); ``accumulate[i]``: add to an existing gradient instead of storing."""
+    n = len(params)
+    arr = (_lib.RegTensor * n)()
+    for i, (p, r) in enumerate(zip(params, refs)):
+        g = grads[i] if grads is not None else None
+        arr[i] = _lib.RegTensor(p.data_ptr(), r.data_ptr(), g.data_ptr() if g is not None else None, p.numel(),
+                                int(bool(accumulate[i])) if accumulate is not None else 0)
+    check(lib.hmvae_l2_reg_fwdbwd(arr, n, float(weight), ptr(loss), stream()), "l2_reg_fwdbwd")
 
 
 def traj_fwdbwd(root_v_pred, root_v_gt, mean3, std3, joints, w_v, w_trans, losses, want_grad=True):

@@ -368,6 +368,25 @@ class TwoHierSAVAEModel(nn.Module):
         out_pose_pos = out_pose_pos.view(bs, self.max_timesteps, self.n_joints, 3)
         return out_cont6d, out_rotation_matrix, out_pose_pos, None, None, None, None
 
+    def _decode_w_given_decoder(self, z_list, curr_decoder):
+        """seq_two_hier_sa_vae.py:501-529."""
+        from .latent_opt import decode_w_given_decoder
+        return decode_w_given_decoder(self, z_list, curr_decoder)
+
+    def l2_masked_criterion(self, pred, gt, mask):
+        """seq_two_hier_sa_vae.py:717-735 -> (mean over all elements of (pred-gt)^2 * mask, per-frame mean [bs, T])."""
+        from .latent_opt import l2_masked_criterion
+        return l2_masked_criterion(pred, gt, mask)
+
+    def optimize_latent(self, target_cont6d, target_rotmat, target_mask, hp=None, z_vec_list=None, prev_epochs=50, opt_it=None,
+                        cuda_graph=True):
+        """The latent-space optimisation loop shared by final_long_seq_try_interpolation (seq_two_hier_sa_vae.py:1356-1429,
+        prev_epochs = 50) and final_motion_completion_long_seq (:1698-1757, prev_epochs = 100) for one window of
+        ``max_timesteps`` frames: targets bs X T X 24 X 6 / bs X T X 24 X 3 X 3, mask bs X T X 24.  See latent_opt.py."""
+        from .latent_opt import optimize_latent
+        return optimize_latent(self, target_cont6d, target_rotmat, target_mask, self.hp if hp is None else hp,
+                               z_vec_list=z_vec_list, prev_epochs=prev_epochs, opt_it=opt_it, cuda_graph=cuda_graph)
+
     def adjust_root_rot(self, ori_seq_data):
         """seq_two_hier_sa_vae.py:531-551: rotate every frame's root so that frame 0 faces the identity."""
         bs, timesteps = ori_seq_data.shape[:2]

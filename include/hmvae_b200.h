@@ -164,6 +164,13 @@ int hmvae_recon_fwdbwd(const float* x6_pred, int ncw, const float* gt_6d, const 
                        const float* offsets, const int* parents, int joints, int batch, int t,
                        float s6, float srot, float spos, float* losses, float* dx6, float* pos_pred_out,
                        float* gt_pos_out, void* stream);
+/* Same kernel with a per-(frame, joint) weight on the squared errors: l2_masked_criterion, seq_two_hier_sa_vae.py:717-735
+ * (mask [B, T, joints], the mean still runs over ALL elements), as used by the latent-space optimisation loops
+ * (:1356-1429, :1698-1757).  mask may be NULL (= hmvae_recon_fwdbwd).  rot_pred_out: optional [B,T,joints,3,3]. */
+int hmvae_recon_masked_fwdbwd(const float* x6_pred, int ncw, const float* gt_6d, const float* gt_rotmat, const float* mask,
+                              const float* offsets, const int* parents, int joints, int batch, int t, float s6, float srot,
+                              float spos, float* losses, float* dx6, float* pos_pred_out, float* gt_pos_out,
+                              float* rot_pred_out, void* stream);
 /* Turns the atomically accumulated sums into loss values on the device, without a host sync:
  * out[i] = acc[i]*scale[i] (i<n), out[n] = sum w[i]*out[i] (total), out[n+1] = sum wk[i]*out[i] (weighted KL); acc is zeroed
  * for the next step.  scale / w / wk are HOST arrays of n <= 8 floats. */
@@ -200,19 +207,32 @@ typedef struct {
   float* v;
   long numel;
 } hmvae_adam_tensor;
-int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2, float eps,
+int hmvae_adam_step(const hmvae_adam_tensor* tensors, int n_tensors, float lr, double beta1, double beta2, float eps,
                     float weight_decay, int step, float grad_scale, void* stream);
 /* Same, but the two step-dependent scalars {lr/(1-b1^t), 1/sqrt(1-b2^t)} are read from DEVICE memory (float[2]) so that
  * a CUDA graph of the whole training step can be replayed while the host advances t and the LR schedule. */
-int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const float* dyn2, float beta1, float beta2,
+int hmvae_adam_step_dyn(const hmvae_adam_tensor* tensors, int n_tensors, const float* dyn2, double beta1, double beta2,
                         float eps, float weight_decay, float grad_scale, void* stream);
+
+/* Decoder-weight L2 regulariser of the latent-space optimisation loops (seq_two_hier_sa_vae.py:1382-1387, 1717-1722; the
+ * per-parameter l2_criterion(params, self.dec.state_dict()[name]) loop): loss[0] += sum_i mean((p_i - p0_i)^2) (atomic; caller
+ * zeroes) and, where g_i is given, g_i (+)= weight * 2 (p_i - p0_i) / numel_i.  accumulate != 0: add to the gradient the
+ * backward pass wrote; 0: store (parameters the backward pass does not reach).  One launch per 64 tensors. */
+typedef struct {
+  const float* p;
+  const float* p0;
+  float* g;
+  long numel;
+  int accumulate;
+} hmvae_reg_tensor;
+int hmvae_l2_reg_fwdbwd(const hmvae_reg_tensor* tensors, int n_tensors, float weight, float* loss, void* stream);
 
 /* The step-dependent scalars produced ON THE DEVICE (replaces torch.optim.Adam's host-side bias corrections and
  * torch.optim.lr_scheduler.StepLR, trainer_motion_vae.py:29-33, 251-262): clock = device uint32[2] {completed Adam steps t,
  * scheduler iterations}; one call advances both and writes dyn2 = {lr_t / (1 - b1^t), 1 / sqrt(1 - b2^t)} with
  * lr_t = base_lr * gamma^(iterations / step_size) (step_size <= 0: constant).  Capturable: a replayed CUDA graph of the step
  * keeps its own time, whatever the host has queued ahead. */
-int hmvae_opt_clock_tick(unsigned int* clock, float base_lr, float gamma, int step_size, float beta1, float beta2,
+int hmvae_opt_clock_tick(unsigned int* clock, float base_lr, float gamma, int step_size, double beta1, double beta2,
                          float* dyn2, void* stream);
 
 /* ------------------------------------------------------------------ batch assembly (utils_motion_vae.py, the step before the path)
@@ -253,7 +273,7 @@ typedef struct {
   float* mc_param;        /* kernel uses multimem.ld_reduce / multimem.st (in-switch reduction and replication); else NULL          */
 } hmvae_dp_peers;
 int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges, const float* dyn2,
-                       float beta1, float beta2, float eps, float weight_decay, float grad_scale, unsigned int* state,
+                       double beta1, double beta2, float eps, float weight_decay, float grad_scale, unsigned int* state,
                        int max_ctas, void* stream);
 /* Peer-memory plumbing over CUDA IPC (used when torch's symmetric memory is unavailable): zero-filled device allocation, its
  * 64-byte handle, and mapping / unmapping of another process's handle. */

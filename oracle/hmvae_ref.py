@@ -164,6 +164,14 @@ def l2_criterion(pred, gt):
     return ((pred - gt) ** 2).mean()
 
 
+def l2_masked_criterion(pred, gt, mask):
+    """seq_two_hier_sa_vae.py:717-735.  pred/gt: bs X T X 24 X {6 | 3 X 3 | 3}; mask: bs X T X 24 -> (loss, [bs, T])."""
+    assert pred.size() == gt.size()
+    m = mask[:, :, :, None] if pred.dim() == 4 else mask[:, :, :, None, None]
+    loss = (pred - gt) ** 2 * m
+    return loss.mean(), loss.reshape(loss.shape[0], loss.shape[1], -1).mean(dim=-1)
+
+
 # --------------------------------------------------------------------------------------
 # parameter construction with the reference's RNG consumption order
 # --------------------------------------------------------------------------------------
@@ -404,6 +412,73 @@ class HMVAEOracle:
             total.reshape(()).backward()
         return dict(total=total.reshape(()), rec_6d=l6d, rec_rot=lrot, rec_pose=lpos,
                     kl_deep=kls[-1].reshape(()), kl_shallow=kls[0].reshape(()), x6=x6, rot=rot, pos=pos)
+
+    def latent_optimise(self, z_init, target_6d, target_rot, mask, hp, prev_epochs=50, opt_it=None):
+        """Inner loop of final_long_seq_try_interpolation (seq_two_hier_sa_vae.py:1356-1429) / final_motion_completion_long_seq
+        (:1698-1757): opt_it iterations; iterations i <= prev_epochs step Adam(z_vec_list, lr=opt_lr), later ones step
+        Adam(curr_decoder.parameters(), lr=opt_lr*0.001) when hp['optimize_decoder'] (curr_decoder = deepcopy(self.dec), which
+        carries the ``dec.enc.*`` encoder copies: they get the regulariser's gradient and weight decay like every other parameter);
+        each optimiser has its own StepLR(opt_step_size, opt_gamma) when opt_lr_policy == 'step' (:40-51).
+
+        z_init: 4 tensors [bs, k_edges, d]; target_6d bs X T X 24 X 6; target_rot bs X T X 24 X 3 X 3; mask bs X T X 24.
+        Uses (and, in the decoder phase, UPDATES a copy of) self.params.  Returns dict(losses [opt_it, 6] = (rec_6d, rec_rot,
+        rec_pose, reg, reg_decoder, total), out_6d / out_rot_mat / out_pose_pos of the LAST iteration, z, decoder_params)."""
+        from torch.optim import lr_scheduler
+
+        opt_it = hp["opt_it"] if opt_it is None else opt_it
+        bs, t = target_6d.shape[0], target_6d.shape[1]
+        j = len(self.parents)
+        with torch.no_grad():
+            target_pos = forward_kinematics(target_rot.reshape(bs * t, j, 3, 3), self.parents, self.offsets).view(bs, t, j, 3)
+        z = [torch.nn.Parameter(v.detach().clone()) for v in z_init]
+        orig = {k: v.detach().clone() for k, v in self.params.items()}
+        # curr_decoder.named_parameters(): dec.* and, through dec.enc, the encoder's (trainable ones)
+        cur = {k: torch.nn.Parameter(v.detach().clone()) for k, v in self.params.items()}
+        saved, self.params = self.params, cur
+        optimize_decoder = bool(hp.get("optimize_decoder", False))
+
+        def sched(opt):
+            if hp.get("opt_lr_policy", "constant") == "step":
+                return lr_scheduler.StepLR(opt, step_size=hp["opt_step_size"], gamma=hp["opt_gamma"])
+            return None
+
+        z_opt = torch.optim.Adam(z, lr=hp["opt_lr"], weight_decay=hp["weight_decay"])
+        z_sched = sched(z_opt)
+        if optimize_decoder:
+            d_opt = torch.optim.Adam(list(cur.values()), lr=hp["opt_lr"] * 0.001, weight_decay=hp["weight_decay"])
+            d_sched = sched(d_opt)
+        hist = []
+        try:
+            for i in range(opt_it):
+                x6, rot, pos = self.decode(z)
+                x6, rot, pos = x6.view(bs, t, j, 6), rot.view(bs, t, j, 3, 3), pos.view(bs, t, j, 3)
+                l6, _ = l2_masked_criterion(x6, target_6d, mask)
+                lrot, _ = l2_masked_criterion(rot, target_rot, mask)
+                lpos, _ = l2_masked_criterion(pos, target_pos, mask)
+                l_reg = l2_criterion(z[0], torch.zeros_like(z[0])) + l2_criterion(z[3], torch.zeros_like(z[3]))
+                l_reg_dec = torch.zeros(1, device=x6.device)
+                if optimize_decoder:
+                    for k, v in cur.items():
+                        l_reg_dec = l_reg_dec + l2_criterion(v, orig[k])
+                total = hp["rec_6d_w"] * l6 + hp["rec_rot_w"] * lrot + hp["rec_pose_w"] * lpos + hp["reg_w"] * l_reg \
+                    + hp["reg_w_decoder"] * l_reg_dec
+                hist.append(torch.stack([l6.detach(), lrot.detach(), lpos.detach(), l_reg.detach(), l_reg_dec.detach().reshape(()),
+                                         total.detach().reshape(())]))
+                dec_phase = optimize_decoder and i > prev_epochs
+                (d_opt if dec_phase else z_opt).zero_grad()
+                total.reshape(()).backward()
+                if dec_phase:
+                    d_opt.step()
+                    if d_sched is not None:
+                        d_sched.step()
+                else:
+                    z_opt.step()
+                    if z_sched is not None:
+                        z_sched.step()
+        finally:
+            self.params = saved
+        return dict(losses=torch.stack(hist), out_6d=x6.detach(), out_rot_mat=rot.detach(), out_pose_pos=pos.detach(),
+                    z=[v.detach() for v in z], decoder_params={k: v.detach() for k, v in cur.items()})
 
     def test_path(self, seq_rot_6d, seq_rot_mat, sampled_z):
         """TwoHierSAVAEModel.test, seq_two_hier_sa_vae.py:560-639 (random_root_rot_flag False).

@@ -1,6 +1,6 @@
 """Multi-GPU parity of the fused data-parallel optimiser step (csrc/dp.cu), driver-visible: spawns W ranks with torchrun when
 >= 2 GPUs are visible (skips otherwise) and runs
-  * tools/dp_kernel_check.py -- kernel-level, tight bounds (reduced gradient 1e-6, moments 1e-5, parameters 2e-7, ranks
+  * tools/dp_kernel_check.py -- kernel-level, tight bounds (reduced gradient 1e-6, moments 1e-5, parameters 5e-7, ranks
     bit-identical), on the unicast peer-load path AND on the NVSwitch multicast (multimem) path;
   * tools/dp_check.py        -- three Trainer steps of the len64 model, fused kernel vs NCCL all-reduce + multi-tensor Adam.
 """

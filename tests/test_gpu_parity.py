@@ -513,7 +513,13 @@ def test_dp_adam_kernel_vs_torch_single_rank():
     for a, b in zip(mine_p, ref_p):
         np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-7)
     sd = opt.state_dict()
-    np.testing.assert_allclose(sd["exp_avg"][0].cpu().numpy(), opt_ref.state[ref_p[0]]["exp_avg"].numpy(), rtol=1e-4, atol=1e-6)
+    assert set(sd) == {"state", "param_groups"} and 2 not in sd["state"]      # torch.optim.Adam layout; no entry without a gradient
+    for i in (0, 1, 3, 4):
+        for key in ("exp_avg", "exp_avg_sq"):
+            np.testing.assert_allclose(sd["state"][i][key].cpu().numpy(), opt_ref.state[ref_p[i]][key].numpy(), rtol=1e-4, atol=1e-6)
+        assert float(sd["state"][i]["step"]) == 4.0
+    opt_ref.load_state_dict({"state": {k: {a: (b.cpu() if torch.is_tensor(b) else b) for a, b in v.items()} for k, v in sd["state"].items()},
+                             "param_groups": sd["param_groups"]})           # and torch accepts it
     ops.unregister_grad_buffers()
 
 
@@ -611,3 +617,82 @@ def test_batch_assemble_vs_reference_golden(smpl, tag):
         want = BR.assemble(big[b], ms, BR.rand_rotation_matrix(1.0, rns[b]))
         for n, v, w in zip(names, outs, want):
             np.testing.assert_allclose(v[b].cpu().numpy(), w, rtol=3e-6, atol=3e-6, err_msg=n)
+
+
+# ------------------------------------------------------------------------------------------------ latent-space optimisation (8f-4)
+def _model_with_oracle_weights(hp, smpl):
+    ora = O.HMVAEOracle(hp, smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])).init(seed=0)
+    model = TwoHierSAVAEModel(dict(hp), device=DEV)
+    sd = model.state_dict()
+    for k, v in ora.params.items():
+        sd[k] = v.detach().clone()
+        if k.startswith("enc.") and "dec." + k in sd:
+            sd["dec." + k] = v.detach().clone()
+    model.load_state_dict(sd)
+    return model.to(DEV), ora
+
+
+def test_l2_masked_criterion_and_masked_recon_kernel(smpl):
+    """l2_masked_criterion (module surface) against the real reference's values, and the fused masked kernel against it."""
+    from test_oracle_golden import HPOPT
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "latent_opt.npz")))
+    model = TwoHierSAVAEModel(dict(HPOPT), device=DEV).to(DEV)
+    loss, saved = model.l2_masked_criterion(cu(g["lmc_pred"]), cu(g["lmc_gt"]), cu(g["lmc_mask"]))
+    np.testing.assert_allclose(float(loss), float(g["lmc_loss"]), rtol=1e-5)
+    np.testing.assert_allclose(saved.cpu().numpy(), g["lmc_saved"], rtol=1e-5, atol=1e-7)
+    # fused kernel: three masked sums + gradient vs autograd through the oracle
+    parents, off = smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])
+    gen = torch.Generator().manual_seed(3)
+    b, t = 3, 8
+    batch = O.synthetic_batch(b, t, parents, off, seed=5)
+    x6 = torch.randn(b, t, 144, generator=gen).requires_grad_(True)
+    mask = (torch.rand(b, t, 24, generator=gen) > 0.4).float()
+    rot = O.rot6d_to_rotmat(x6.view(b * t, 24, 6))
+    pos = O.forward_kinematics(rot, parents, off)
+    gpos = O.forward_kinematics(batch["seq_rot_mat"].view(b * t, 24, 3, 3), parents, off)
+    l6, _ = O.l2_masked_criterion(x6.view(b, t, 24, 6), batch["seq_rot_6d"].view(b, t, 24, 6), mask)
+    lr, _ = O.l2_masked_criterion(rot.view(b, t, 24, 3, 3), batch["seq_rot_mat"].view(b, t, 24, 3, 3), mask)
+    lp, _ = O.l2_masked_criterion(pos.view(b, t, 24, 3), gpos.view(b, t, 24, 3), mask)
+    (1.0 * l6 + 1.0 * lr + 10.0 * lp).backward()
+    acc = torch.zeros(4, device=DEV)
+    rot_out, pos_out = torch.empty(b, t, 24, 3, 3, device=DEV), torch.empty(b, t, 24, 3, device=DEV)
+    dx = ops.recon_fwdbwd(x6.detach().to(DEV), False, batch["seq_rot_6d"].to(DEV), batch["seq_rot_mat"].to(DEV), off.to(DEV), parents,
+                          1.0, 1.0, 10.0, acc, mask=mask.to(DEV), rot_out=rot_out, pos_out=pos_out)
+    n = float(b * t * 24)
+    np.testing.assert_allclose((acc[:3].cpu() / torch.tensor([n * 6, n * 9, n * 3])).numpy(), [float(l6), float(lr), float(lp)], rtol=1e-5)
+    assert rel_l2(dx.cpu(), x6.grad) < 1e-5
+    assert rel_l2(rot_out.cpu(), rot.detach().view(b, t, 24, 3, 3)) < 1e-5 and rel_l2(pos_out.cpu(), pos.detach().view(b, t, 24, 3)) < 1e-5
+
+
+@pytest.mark.parametrize("impl,graph,tol", [(ops.IMPL_SIMT, False, 2e-4), (ops.IMPL_AUTO, True, 2e-3)])
+def test_latent_optimisation_vs_reference_golden(impl, graph, tol, smpl):
+    """TwoHierSAVAEModel.optimize_latent against the loop body run with the REAL reference modules
+    (oracle/make_golden_latent_opt.py; seq_two_hier_sa_vae.py:1356-1429): 3 iterations on the latents, 4 on the decoder copy, StepLR
+    boundaries in both phases.  fp32 CUDA-core path eagerly at 2e-4, tcgen05 TF32 path as two CUDA graphs at 2e-3."""
+    from test_oracle_golden import latent_opt_problem
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "latent_opt.npz")))
+    hp, prev_epochs, t6, tR, mask, z_init = latent_opt_problem(g, smpl)
+    model, _ = _model_with_oracle_weights(hp, smpl)
+    ops.set_conv_impl(impl)
+    try:
+        res = model.optimize_latent(t6.to(DEV), tR.to(DEV), mask.to(DEV), hp, z_vec_list=z_init, prev_epochs=prev_epochs, cuda_graph=graph)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_conv_impl(ops.IMPL_AUTO)
+    hist = res["losses"].cpu().numpy()
+    ref = g["losses"]
+    np.testing.assert_allclose(hist[:, [0, 1, 2, 3, 5]], ref[:, [0, 1, 2, 3, 5]], rtol=tol, atol=1e-8)
+    np.testing.assert_allclose(hist[:, 4], ref[:, 4], rtol=20 * tol, atol=1e-9)          # regulariser: sum of ~1e-7 drifts
+    for k in range(4):
+        np.testing.assert_allclose(res["z_vec_list"][k].cpu().numpy(), g[f"z_final{k}"], rtol=10 * tol, atol=50 * tol)
+    assert rel_l2(res["out_6d"].cpu(), g["out_6d"]) < tol
+    assert rel_l2(res["out_rot_mat"].cpu(), g["out_rot_mat"]) < tol
+    assert rel_l2(res["out_pose_pos"].cpu(), g["out_pose_pos"]) < tol
+    # the decoder copy moved (and the model's own decoder did not)
+    moved = dict(res["decoder"].named_parameters())
+    for k, p in model.dec.named_parameters():
+        if not p.requires_grad:
+            continue
+        d = (moved[k].detach() - p.detach()).cpu()
+        refd = g[f"dec_delta/{k}"]
+        np.testing.assert_allclose(float(d.abs().sum()), refd[1], rtol=max(20 * tol, 2e-2), atol=1e-7, err_msg=k)

@@ -174,3 +174,55 @@ def test_aa2rot_against_scipy():
     np.testing.assert_allclose(r[:, :3, :3].numpy(), ref, atol=2e-5)
     small = O.angle_axis_to_rotation_matrix(torch.tensor([[1e-4, -2e-4, 3e-4]]))
     np.testing.assert_allclose(small[0, :3, :3].numpy(), [[1, -3e-4, -2e-4], [3e-4, 1, -1e-4], [2e-4, 1e-4, 1]], atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ latent-space optimisation (8f-4)
+HPOPT = dict(HP64, weight_decay=1e-4, opt_lr=0.1, opt_it=150, reg_w=0, reg_w_decoder=1000, opt_lr_policy="step", opt_step_size=50,
+             opt_gamma=0.1, interpolation_window=5, optimize_decoder=True)
+
+
+@pytest.fixture(scope="module")
+def golden_latent_opt():
+    import os
+
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "latent_opt.npz")))
+
+
+def latent_opt_problem(g, smpl):
+    """Inputs of the golden run (oracle/make_golden_latent_opt.py): hp overrides, targets, mask, initial latents."""
+    opt_it, step_size, prev_epochs = [int(v) for v in g["hp_overrides"]]
+    hp = dict(HPOPT, opt_it=opt_it, opt_step_size=step_size)
+    off = torch.from_numpy(smpl["offsets"])
+    batch = O.synthetic_batch(2, 64, smpl["parents"].tolist(), off, seed=int(g["seed_batch"]))
+    z_init = [torch.from_numpy(g[f"z_init{k}"]) for k in range(4)]
+    return hp, prev_epochs, batch["seq_rot_6d"].view(2, 64, 24, 6), batch["seq_rot_mat"].view(2, 64, 24, 3, 3), \
+        torch.from_numpy(g["target_mask"]), z_init
+
+
+def test_l2_masked_criterion_vs_reference(golden_latent_opt):
+    g = golden_latent_opt
+    loss, saved = O.l2_masked_criterion(torch.from_numpy(g["lmc_pred"]), torch.from_numpy(g["lmc_gt"]), torch.from_numpy(g["lmc_mask"]))
+    np.testing.assert_allclose(float(loss), float(g["lmc_loss"]), rtol=1e-6)
+    np.testing.assert_allclose(saved.numpy(), g["lmc_saved"], rtol=1e-6, atol=1e-7)
+
+
+def test_latent_optimisation_vs_reference(golden_latent_opt, smpl):
+    """The oracle's restatement of the loop (seq_two_hier_sa_vae.py:1356-1429) against the loop body run with the REAL reference
+    modules: losses of every iteration (latent phase, then decoder phase, StepLR boundaries inside both), final latents, final
+    outputs, and the drift of every decoder-copy parameter."""
+    g = golden_latent_opt
+    hp, prev_epochs, t6, tR, mask, z_init = latent_opt_problem(g, smpl)
+    ora = O.HMVAEOracle(hp, smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])).init(seed=0)
+    res = ora.latent_optimise(z_init, t6, tR, mask, hp, prev_epochs=prev_epochs)
+    np.testing.assert_allclose(res["losses"].numpy(), g["losses"], rtol=2e-4, atol=1e-9)
+    for k in range(4):
+        np.testing.assert_allclose(res["z"][k].numpy(), g[f"z_final{k}"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(res["out_6d"].numpy(), g["out_6d"], atol=5e-5)
+    np.testing.assert_allclose(res["out_rot_mat"].numpy(), g["out_rot_mat"], atol=5e-5)
+    np.testing.assert_allclose(res["out_pose_pos"].numpy(), g["out_pose_pos"], atol=5e-5)
+    for k, v in res["decoder_params"].items():
+        name = k[4:] if k.startswith("dec.") else "enc." + k[4:]        # curr_decoder's own naming: dec.X -> X, enc.X -> enc.X
+        mine, ref = _cks(v), g[f"dec_final/{name}"]
+        assert abs(mine[0] - ref[0]) <= 1e-6 * ref[1] + 1e-6, k          # the plain sum cancels: compare on the abs-sum scale
+        np.testing.assert_allclose(mine[1:], ref[1:], rtol=1e-5, atol=1e-6, err_msg=k)
+        np.testing.assert_allclose(_cks(v - ora.params[k].detach())[1:], g[f"dec_delta/{name}"][1:], rtol=5e-3, atol=1e-7, err_msg=k)

@@ -8,7 +8,7 @@ gradients: G = ((g_0 + g_1) + ...) * (1/W) in fp32, then torch.optim.Adam.  With
 (an update is +-lr whatever the magnitude of a rounding-level gradient), so the bounds are tight:
     reduced gradient before Adam (recovered from exp_avg after step 1: m_1 = (1-b1) * (G + wd*p))   <= 1e-6 relative-L2
     exp_avg / exp_avg_sq after 3 steps                                                              <= 1e-5 relative-L2
-    parameters after 3 steps                                                                        <= 2e-7 absolute
+    parameters after 3 steps                                             <= 5e-7 absolute (2 ulp of the largest |p| ~ 4; one update = 1e-4)
     all ranks hold bit-identical parameters.
 Exit code 0 = pass.  tests/test_dp_multi_gpu.py spawns this when >= 2 GPUs are visible."""
 import os
@@ -87,7 +87,7 @@ for i, (a, b) in enumerate(zip(mine, ref_p)):
     em, ev = rel_l2(sd["state"][i]["exp_avg"], ref.state[b]["exp_avg"]), rel_l2(sd["state"][i]["exp_avg_sq"], ref.state[b]["exp_avg_sq"])
     if em > 1e-5 or ev > 1e-5:
         fails.append("tensor %d: exp_avg rel-L2 %.3e, exp_avg_sq rel-L2 %.3e" % (i, em, ev))
-    if d > 2e-7:
+    if d > 5e-7:
         fails.append("tensor %d: parameter max abs diff %.3e" % (i, d))
 if DEAD in sd["state"]:
     fails.append("dead parameter has optimiser state")
