@@ -84,6 +84,7 @@ _SIGS = {
     "hmvae_launch_count": (c_longlong, []),
     "hmvae_conv_plan_create": (c_int, [POINTER(ConvDesc), IP, IP, IP, POINTER(c_void_p)]),
     "hmvae_conv_plan_destroy": (None, [c_void_p]),
+    "hmvae_conv_tc_debug": (c_int, [P]),
     "hmvae_conv_fprop": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_conv_dgrad": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_conv_wgrad": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),

@@ -52,7 +52,15 @@ struct TcArgs {
   int splits, split_len;   // split-K: gridDim.z CTAs per (tile, group), each handles split_len consecutive stages
   int groups, dcols;       // joint groups (gridDim.y); accumulator columns per group (= GJ * n_pad) in the dump
   const struct TcWorkG* wtab;   // [groups] host-built work tables (device memory, owned by the plan)
+  unsigned long long* dbg;      // optional (tools/tc_phases.py): 8 globaltimer stamps per CTA
 };
+static unsigned long long* g_tc_dbg = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(i) do { if (p.dbg) p.dbg[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = gtimer(); } while (0)
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -249,6 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   pdl_trigger();
   const ConvArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) TC_STAMP(0);
   const int mt = blockIdx.x;
   const int j0 = blockIdx.y * p.GJ;
   const int gj = (a.J - j0 < p.GJ) ? a.J - j0 : p.GJ;
@@ -292,6 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
   __syncthreads();
   tc_fence_after();
   pdl_wait();       // prologue done (barriers, TMEM, work table = plan constants): now wait for the producer of astage / wp
+  if (tid == 0) TC_STAMP(1);
   const uint32_t slot_u = (uint32_t)p.n_pad;                 // 16-byte units per slot inside one (tap, chunk) row block
   const int si_beg = blockIdx.z * p.split_len, si_end = si_beg + p.split_len;
 
@@ -330,6 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
+          if (si == si_beg) TC_STAMP(2);
           const uint32_t a_base = smem_u32(smem_raw + (size_t)s * p.stage_bytes);
           const uint32_t b_base = a_base + p.a_bytes;
           // Descriptors: only the 14-bit start-address field (16-byte units, low word) changes between MMAs, and between
@@ -386,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
-    if (lane == 0) tc_commit(&accum_bar);
+    if (lane == 0) { tc_commit(&accum_bar); TC_STAMP(3); }
     __syncwarp();
   } else {
     // =============================== epilogue (warps 2..5): TMEM -> accumulator dump ===============================
@@ -396,6 +407,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
     // CTA at B=32).  Layout conversion, split-K sum, bias / LeakyReLU / pooling / reflect fold happen in conv_tc_finish_kernel.
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
+    if (tid == 64) TC_STAMP(4);
     const int lq = warp & 3;
     const int m = lq * 32 + lane;
     float4* drow = reinterpret_cast<float4*>(dst + ((((size_t)blockIdx.z * p.mtiles + mt) * p.groups + blockIdx.y) * 128 + m) * p.dcols);
@@ -408,8 +420,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
     }
   }
   // ---- teardown
+  if (tid == 64) TC_STAMP(5);
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) TC_STAMP(6);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -766,6 +780,7 @@ int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, cons
                    const float* bias, float* dst, int B, int T, void* workspace, long workspace_bytes, cudaStream_t st) {
   TcArgs p;
   if (!tc_geometry(plan, B, T, mode, &p)) return fail_arg("conv (tcgen05): unsupported geometry");
+  p.dbg = g_tc_dbg;
   const long need = tc_stage_ws(p) + tc_part_ws(p);
   if (!workspace || workspace_bytes < need) return fail_arg("conv (tcgen05): workspace too small");
   float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + tc_stage_ws(p));
@@ -792,3 +807,10 @@ int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, cons
 }
 
 }  // namespace hmvae
+
+// tools/tc_phases.py: device buffer of 8 x uint64 per CTA that receives globaltimer stamps of the next conv_tc launches
+// (0 entry, 1 prologue done, 2 first stage landed, 3 last MMA issued, 4 accumulators complete, 5 dump stored, 6 exit); NULL = off.
+extern "C" int hmvae_conv_tc_debug(void* buf) {
+  hmvae::g_tc_dbg = reinterpret_cast<unsigned long long*>(buf);
+  return 0;
+}

@@ -200,7 +200,10 @@ def _workspace(plan, b, t_in, mode, device):
 
 
 def _tc_ok(plan, b, t_in, mode):
-    return _conv_impl != IMPL_SIMT and bool(lib.hmvae_conv_tc_supported(plan.handle, b, t_in, mode))
+    """``plan.exact`` (set from SkeletonConv.exact): this layer always takes the fp32 CUDA-core kernels."""
+    if _conv_impl == IMPL_SIMT or getattr(plan, "exact", False):
+        return False
+    return bool(lib.hmvae_conv_tc_supported(plan.handle, b, t_in, mode))
 
 
 class _SkeletonConvFn(Function):
@@ -220,7 +223,7 @@ class _SkeletonConvFn(Function):
             y = torch.empty(shape, device=x.device, dtype=torch.float32)
         w = weight.contiguous()
         tc_f, tc_d = _tc_ok(plan, b, t_in, 0), _tc_ok(plan, b, t_in, 1)
-        if _conv_impl == IMPL_TC and not tc_f:
+        if _conv_impl == IMPL_TC and not tc_f and not getattr(plan, "exact", False):
             raise _lib.HmvaeError("conv_fprop: the tcgen05 path does not support this geometry")
         wp_d = None
         if tc_f or tc_d:
@@ -270,7 +273,8 @@ class _SkeletonConvFn(Function):
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 gb = grad_buffer(ctx.bias_ref) if ctx.has_bias else None
                 ws = None
-                if _wgrad_tc and _conv_impl != IMPL_SIMT and lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in):
+                if _wgrad_tc and _conv_impl != IMPL_SIMT and not getattr(plan, "exact", False) \
+                        and lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in):
                     gw = grad_buffer(w, zero=True)            # masked blocks are never written: they must read 0
                     n = int(lib.hmvae_conv_wgrad_tc_workspace(plan.handle, b, t_in))
                     ws = torch.empty((n + 3) // 4, device=x.device, dtype=torch.float32)

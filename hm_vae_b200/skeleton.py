@@ -138,6 +138,7 @@ class SkeletonConv(nn.Module):
             p = ops.ConvPlan(self.neighbour_list, self.in_channels_per_joint, self.out_channels_per_joint, self.kernel_size,
                              self.stride, self.padding, self.padding_mode, **fused)
             self._plans[key] = p
+        p.exact = bool(getattr(self, "exact", False))     # per-layer precision override: fp32 CUDA-core kernels instead of TF32
         return p
 
     def forward(self, input):

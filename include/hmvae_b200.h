@@ -96,6 +96,9 @@ int hmvae_conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float
                         int batch, int t_in, void* workspace, long workspace_bytes, void* stream);
 int hmvae_conv_dgrad_tc(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* wp_dgrad, float* dxin,
                         int batch, int t_in, void* workspace, long workspace_bytes, void* stream);
+/* Debug aid (tools/tc_phases.py): device buffer (8 x uint64 per CTA) that receives %globaltimer stamps from the following
+ * hmvae_conv_{fprop,dgrad}_tc launches; NULL switches it off. */
+int hmvae_conv_tc_debug(void* buf);
 
 /* Weight gradient on the tensor cores.  Only unmasked blocks of dw are written (deterministically, one writer per element);
  * masked entries keep their previous value, which must be 0.  accumulate != 0 adds into dw / dbias. */
