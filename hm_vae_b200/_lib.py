@@ -64,6 +64,13 @@ class AdamTensor(Structure):
     _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("numel", c_long)]
 
 
+class ConvLinkDesc(Structure):
+    _fields_ = [("kind", c_int), ("batch", c_int), ("prod", c_void_p), ("prod_t", c_int), ("cons", c_void_p), ("cons_t", c_int),
+                ("act", c_int), ("pool_joints", c_int), ("pool_off", POINTER(c_int)), ("pool_idx", POINTER(c_int)),
+                ("dump", c_void_p), ("bias", c_void_p), ("aux", c_void_p), ("add", c_void_p), ("sact", c_void_p),
+                ("yact_c", c_void_p), ("s_out", c_void_p), ("stage_ws", c_void_p)]
+
+
 class RegTensor(Structure):
     _fields_ = [("p", c_void_p), ("p0", c_void_p), ("g", c_void_p), ("numel", c_long), ("accumulate", c_int)]
 
@@ -85,6 +92,12 @@ _SIGS = {
     "hmvae_conv_plan_create": (c_int, [POINTER(ConvDesc), IP, IP, IP, POINTER(c_void_p)]),
     "hmvae_conv_plan_destroy": (None, [c_void_p]),
     "hmvae_conv_tc_debug": (c_int, [P]),
+    "hmvae_conv_tc_sizes": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_long), POINTER(c_long)]),
+    "hmvae_conv_tc_stage": (c_int, [c_void_p, c_int, P, P, c_int, c_int, P, P]),
+    "hmvae_conv_tc_run": (c_int, [c_void_p, c_int, P, c_int, c_int, P, P, P]),
+    "hmvae_conv_tc_finish": (c_int, [c_void_p, c_int, P, P, P, c_int, c_int, P]),
+    "hmvae_conv_link_supported": (c_int, [POINTER(ConvLinkDesc)]),
+    "hmvae_conv_link": (c_int, [POINTER(ConvLinkDesc), P]),
     "hmvae_conv_fprop": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_conv_dgrad": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_conv_wgrad": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),

@@ -40,6 +40,13 @@ int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* w
 int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, const float* wp,
                    const float* bias, float* dst, int B, int T, void* workspace, long workspace_bytes, cudaStream_t st);
 long conv_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T, int mode);
+bool conv_tc_sizes(const hmvae_conv_plan* plan, int B, int T, int mode, long* stage_bytes, long* dump_bytes);
+int conv_tc_stage(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, int B, int T, void* stage_ws,
+                  cudaStream_t st);
+int conv_tc_run(const hmvae_conv_plan* plan, int mode, const float* wp, int B, int T, const void* stage_ws, void* dump_ws,
+                cudaStream_t st);
+int conv_tc_finish(const hmvae_conv_plan* plan, int mode, const void* dump_ws, const float* bias, float* dst, int B, int T,
+                   cudaStream_t st);
 void conv_tc_release(const hmvae_conv_plan* plan);
 bool conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int B, int T);
 long conv_wgrad_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T);
@@ -169,6 +176,37 @@ extern "C" int hmvae_conv_pack_weights(const hmvae_conv_plan* plan, const float*
 extern "C" long hmvae_conv_tc_workspace(const hmvae_conv_plan* plan, int batch, int t_in, int mode) {
   if (!plan || batch < 1 || t_in < 1 || (mode != 0 && mode != 1)) return -1;
   return conv_tc_workspace_bytes(plan, batch, t_in, mode);
+}
+
+extern "C" int hmvae_conv_tc_sizes(const hmvae_conv_plan* plan, int batch, int t_in, int mode, long* stage_bytes,
+                                   long* dump_bytes) {
+  if (!plan || !stage_bytes || !dump_bytes || batch < 1 || t_in < 1 || (mode != 0 && mode != 1)) return 0;
+  if (check_shape(plan, batch, t_in, "conv_tc_sizes")) return 0;
+  return conv_tc_sizes(plan, batch, t_in, mode, stage_bytes, dump_bytes) ? 1 : 0;
+}
+
+extern "C" int hmvae_conv_tc_stage(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, int batch,
+                                   int t_in, void* stage_ws, void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_tc_stage");
+  if (rc) return rc;
+  if (!src || (mode != 0 && mode != 1) || (mode == 1 && plan->d.lrelu && !yact)) return fail_arg("conv_tc_stage: bad arguments");
+  return conv_tc_stage(plan, mode, src, yact, batch, t_in, stage_ws, (cudaStream_t)stream);
+}
+
+extern "C" int hmvae_conv_tc_run(const hmvae_conv_plan* plan, int mode, const float* wp, int batch, int t_in,
+                                 const void* stage_ws, void* dump_ws, void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_tc_run");
+  if (rc) return rc;
+  if (!wp || (mode != 0 && mode != 1)) return fail_arg("conv_tc_run: bad arguments");
+  return conv_tc_run(plan, mode, wp, batch, t_in, stage_ws, dump_ws, (cudaStream_t)stream);
+}
+
+extern "C" int hmvae_conv_tc_finish(const hmvae_conv_plan* plan, int mode, const void* dump_ws, const float* bias, float* dst,
+                                    int batch, int t_in, void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_tc_finish");
+  if (rc) return rc;
+  if (!dump_ws || !dst || (mode != 0 && mode != 1)) return fail_arg("conv_tc_finish: bad arguments");
+  return conv_tc_finish(plan, mode, dump_ws, bias, dst, batch, t_in, (cudaStream_t)stream);
 }
 
 extern "C" int hmvae_conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float* wp_fprop, const float* bias,

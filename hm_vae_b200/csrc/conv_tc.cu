@@ -26,48 +26,18 @@
 // together with bias / LeakyReLU.
 #include <string.h>
 
-#include "conv_common.cuh"
+#include "conv_tc.cuh"
 
 namespace hmvae {
+
+static unsigned long long* g_tc_dbg = nullptr;
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_MAX_GJ = 32;
 constexpr int TC_MAX_NB = 16;
 
-struct TcArgs {
-  ConvArgs a;
-  int mode;            // 0 fprop, 1 dgrad
-  int n_real, n_pad;   // N-side channels per joint (real, padded to 16)
-  int ck, ck_pad;      // reduction channels per K-side joint (real, padded to 8)
-  int KC;              // reduction channels per pipeline stage (multiple of 8, divides ck_pad)
-  int Bt, Tt;          // sequences per tile, rows-per-sequence (M = Tt*Bt <= 128)
-  int rows_alloc;      // rows per 16-byte chunk column of an activation tile
-  int Tp2;             // fprop stride 2: rows per phase / Bt
-  int ntt, U;          // dgrad time tiling (T + 2p > 128): tiles per sequence (1 = none), result time steps owned by a tile
-  int GJ, nbmax, stages;
-  int B, T, T_out, mtiles;
-  int a_bytes, stage_bytes;
-  int tmem_cols;
-  int splits, split_len;   // split-K: gridDim.z CTAs per (tile, group), each handles split_len consecutive stages
-  int groups, dcols;       // joint groups (gridDim.y); accumulator columns per group (= GJ * n_pad) in the dump
-  const struct TcWorkG* wtab;   // [groups] host-built work tables (device memory, owned by the plan)
-  unsigned long long* dbg;      // optional (tools/tc_phases.py): 8 globaltimer stamps per CTA
-};
-static unsigned long long* g_tc_dbg = nullptr;
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define TC_STAMP(i) do { if (p.dbg) p.dbg[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = gtimer(); } while (0)
-
 // ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return u;
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -97,24 +67,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// dgrad time tiling: a tile is a window of 128 consecutive rows (padded input positions) of ONE sequence.  Tile tt owns the
-// result steps u in [tt*U, (tt+1)*U); its window starts at 0 for the first tile, ends at Tq for the last one (so that the rows the
-// reflect-padding fold needs are inside), and is centred on the owned rows otherwise.
-__host__ __device__ __forceinline__ int tc_tile_t0(int tt, int ntt, int U, int pad, int Tq) {
-  if (ntt <= 1 || tt == 0) return 0;
-  if (tt == ntt - 1) return Tq - 128;
-  int t0 = tt * U + pad - (128 - U) / 2;
-  if (t0 < 0) t0 = 0;
-  if (t0 > Tq - 128) t0 = Tq - 128;
-  return t0;
-}
-
-__device__ __forceinline__ long tc_out_index(const ConvArgs& a, long b, int j, int o, int t, int T_out) {
-  const int ch = j * a.ojs + a.oco + o;
-  const long ctot = (long)a.J * a.ojs;
-  return a.cl ? (b * T_out + t) * ctot + ch : (b * ctot + ch) * T_out + t;
 }
 
 // ---------------------------------------------------------------------------------------------- weight packing
@@ -434,45 +386,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p, const 
 //   fprop: y[b, j, o, t]  = act(sum_z dump[z][tile(b)][group(j)][t*Bt + b'][jl*n_pad + o] + bias)
 //   dgrad: dx[b, n, c, u] = sum_z (row(u + p) + reflect-fold rows) of the same dump
 // The split-K partial sums are added in a fixed order (deterministic).
-__device__ __forceinline__ float tc_dump_sum(const TcArgs& p, const float* __restrict__ dump, int mt, int g, int row, int col) {
-  const size_t zstride = (size_t)p.mtiles * p.groups * 128 * p.dcols;
-  const float* d = dump + (((size_t)mt * p.groups + g) * 128 + row) * p.dcols + col;
-  float v = 0.f;
-  for (int z = 0; z < p.splits; ++z) v += d[z * zstride];
-  return v;
-}
-
-// fprop result before the activation: conv sum + bias of conv-output joint j, channel o, sequence b, step t
-__device__ __forceinline__ float tc_fprop_value(const TcArgs& p, const float* __restrict__ dump, const float* __restrict__ bias,
-                                                int b, int j, int o, int t) {
-  const int mt = b / p.Bt;
-  float v = tc_dump_sum(p, dump, mt, j / p.GJ, t * p.Bt + (b - mt * p.Bt), (j % p.GJ) * p.n_pad + o);
-  if (bias) v += bias[j * p.a.co + o];
-  return v;
-}
-
-// dgrad result: gradient w.r.t. the (virtual) conv input of joint n, channel c, sequence b, step u (padding adjoint folded in)
-__device__ __forceinline__ float tc_dgrad_value(const TcArgs& p, const float* __restrict__ dump, int b, int n, int c, int u) {
-  const ConvArgs& a = p.a;
-  int mt, bl, t0 = 0;
-  if (p.ntt > 1) {
-    const int tt = u / p.U;
-    mt = b * p.ntt + tt;
-    bl = 0;
-    t0 = tc_tile_t0(tt, p.ntt, p.U, a.p, p.T + 2 * a.p);
-  } else {
-    mt = b / p.Bt;
-    bl = b - mt * p.Bt;
-  }
-  const int g = n / p.GJ, col = (n % p.GJ) * p.n_pad + c;
-  float v = tc_dump_sum(p, dump, mt, g, (u + a.p - t0) * p.Bt + bl, col);
-  if (a.pad_mode == 1) {
-    if (u >= 1 && u <= a.p) v += tc_dump_sum(p, dump, mt, g, (a.p - u - t0) * p.Bt + bl, col);
-    if (u <= p.T - 2 && u >= p.T - 1 - a.p) v += tc_dump_sum(p, dump, mt, g, (a.p + 2 * (p.T - 1) - u - t0) * p.Bt + bl, col);
-  }
-  return v;
-}
-
 __global__ void __launch_bounds__(256) conv_tc_finish_kernel(TcArgs p, const float* __restrict__ dump, const float* __restrict__ bias,
                                                              float* __restrict__ dst) {
   pdl_trigger();
@@ -642,7 +555,7 @@ void conv_tc_release(const hmvae_conv_plan* plan) {
 static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out);
 
 // geometry is a pure function of (plan, mode, B, T): memoised, so the per-call host cost is one map lookup
-static bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out) {
+bool tc_geometry(const hmvae_conv_plan* plan, int B, int T, int mode, TcArgs* out) {
   static thread_local std::map<std::pair<unsigned long long, long>, std::pair<bool, TcArgs>> cache;
   const auto key = std::make_pair(plan->uid, ((long)mode << 48) | ((long)B << 20) | (long)T);
   auto it = cache.find(key);
@@ -746,8 +659,8 @@ bool conv_tc_supported(const hmvae_conv_plan* plan, int B, int T, int mode) {
   return tc_geometry(plan, B, T, mode, &p);
 }
 
-static long tc_stage_ws(const TcArgs& p) { return (long)p.mtiles * p.a.J * (p.ck_pad / p.KC) * p.a_bytes; }
-static long tc_part_ws(const TcArgs& p) {      // accumulator dump [splits][mtiles][groups][128][dcols]
+long tc_stage_ws(const TcArgs& p) { return (long)p.mtiles * p.a.J * (p.ck_pad / p.KC) * p.a_bytes; }
+long tc_part_ws(const TcArgs& p) {      // accumulator dump [splits][mtiles][groups][128][dcols]
   return (long)p.splits * p.mtiles * p.groups * 128 * p.dcols * 4;
 }
 
@@ -755,6 +668,14 @@ long conv_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T, int mode
   TcArgs p;
   if (!tc_geometry(plan, B, T, mode, &p)) return -1;
   return tc_stage_ws(p) + tc_part_ws(p);
+}
+
+bool conv_tc_sizes(const hmvae_conv_plan* plan, int B, int T, int mode, long* stage_bytes, long* dump_bytes) {
+  TcArgs p;
+  if (!tc_geometry(plan, B, T, mode, &p)) return false;
+  *stage_bytes = tc_stage_ws(p);
+  *dump_bytes = tc_part_ws(p);
+  return true;
 }
 
 void conv_packed_sizes(const hmvae_conv_plan* plan, long* n_fprop, long* n_dgrad) {
@@ -776,34 +697,62 @@ int conv_pack(const hmvae_conv_plan* plan, const float* w, float* wp_f, float* w
   return check_launch("conv_pack");
 }
 
+// The three phases of one conv, separately launchable (the stack-level path in ops.py replaces `stage` and `finish` of
+// neighbouring layers by ONE link kernel, conv_link.cu).
+int conv_tc_stage(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, int B, int T, void* stage_ws,
+                  cudaStream_t st) {
+  TcArgs p;
+  if (!tc_geometry(plan, B, T, mode, &p)) return fail_arg("conv (tcgen05): unsupported geometry");
+  if (!stage_ws || !aligned16(stage_ws)) return fail_arg("conv (tcgen05): staging workspace missing / misaligned");
+  const int Tq = T + 2 * p.a.p;
+  const long items = (long)p.mtiles * p.a.J * (p.ck_pad / 4) * p.Bt * (mode == 0 ? Tq : Tq + p.a.K - 1);
+  long blocks = (items + 255) / 256, cap = (long)num_sms() * 8;
+  launch_pdl(conv_tc_prep_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, src, yact,
+             reinterpret_cast<float4*>(stage_ws));
+  return check_launch("conv_tc_prep");
+}
+
+int conv_tc_run(const hmvae_conv_plan* plan, int mode, const float* wp, int B, int T, const void* stage_ws, void* dump_ws,
+                cudaStream_t st) {
+  TcArgs p;
+  if (!tc_geometry(plan, B, T, mode, &p)) return fail_arg("conv (tcgen05): unsupported geometry");
+  p.dbg = g_tc_dbg;
+  if (!stage_ws || !dump_ws || !aligned16(stage_ws) || !aligned16(dump_ws) || !aligned16(wp))
+    return fail_arg("conv (tcgen05): workspace / packed weights must be 16-byte aligned");
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  static thread_local size_t smem_set = 0;      // the attribute is sticky: raise it only when a larger ring shows up
+  if (smem > smem_set) {
+    HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid(p.mtiles, p.groups, p.splits);
+  launch_pdl<true>(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, p, reinterpret_cast<const unsigned char*>(stage_ws), wp,
+                   (const float*)nullptr, reinterpret_cast<float*>(dump_ws));
+  return check_launch(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
+}
+
+int conv_tc_finish(const hmvae_conv_plan* plan, int mode, const void* dump_ws, const float* bias, float* dst, int B, int T,
+                   cudaStream_t st) {
+  TcArgs p;
+  if (!tc_geometry(plan, B, T, mode, &p)) return fail_arg("conv (tcgen05): unsupported geometry");
+  const long per = (long)p.B * p.a.J * p.n_real * (mode == 0 ? p.T_out : p.T);
+  long blocks = (per + 255) / 256, cap = (long)num_sms() * 8;
+  launch_pdl(conv_tc_finish_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, (const float*)dump_ws, bias, dst);
+  return check_launch("conv_tc_finish");
+}
+
 int conv_tc_launch(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, const float* wp,
                    const float* bias, float* dst, int B, int T, void* workspace, long workspace_bytes, cudaStream_t st) {
   TcArgs p;
   if (!tc_geometry(plan, B, T, mode, &p)) return fail_arg("conv (tcgen05): unsupported geometry");
-  p.dbg = g_tc_dbg;
   const long need = tc_stage_ws(p) + tc_part_ws(p);
   if (!workspace || workspace_bytes < need) return fail_arg("conv (tcgen05): workspace too small");
-  float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + tc_stage_ws(p));
-  if (!aligned16(workspace) || !aligned16(wp)) return fail_arg("conv (tcgen05): workspace / packed weights must be 16-byte aligned");
-  {
-    const int Tq = T + 2 * p.a.p;
-    const long items = (long)p.mtiles * p.a.J * (p.ck_pad / 4) * p.Bt * (mode == 0 ? Tq : Tq + p.a.K - 1);
-    long blocks = (items + 255) / 256, cap = (long)num_sms() * 8;
-    launch_pdl(conv_tc_prep_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, src, yact,
-               reinterpret_cast<float4*>(workspace));
-    int rc = check_launch("conv_tc_prep");
-    if (rc) return rc;
-  }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(p.mtiles, p.groups, p.splits);
-  launch_pdl<true>(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, p, reinterpret_cast<const unsigned char*>(workspace), wp, bias, part);
-  int rc = check_launch(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
+  void* part = reinterpret_cast<unsigned char*>(workspace) + tc_stage_ws(p);
+  int rc = conv_tc_stage(plan, mode, src, yact, B, T, workspace, st);
   if (rc) return rc;
-  const long per = (long)p.B * p.a.J * p.n_real * (mode == 0 ? p.T_out : p.T);
-  long blocks = (per + 255) / 256, cap = (long)num_sms() * 8;
-  launch_pdl(conv_tc_finish_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, (const float*)part, bias, dst);
-  return check_launch("conv_tc_finish");
+  rc = conv_tc_run(plan, mode, wp, B, T, workspace, part, st);
+  if (rc) return rc;
+  return conv_tc_finish(plan, mode, part, bias, dst, B, T, st);
 }
 
 }  // namespace hmvae

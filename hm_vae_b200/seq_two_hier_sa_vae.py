@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, stack
 from .fk_layer import ForwardKinematicsLayer, load_smpl24
 from .skeleton import SkeletonConv, SkeletonPool, SkeletonUnpool, find_neighbor, get_edges
 
@@ -107,8 +107,9 @@ class Encoder(nn.Module):
 
         ``needed``: optional set of level indices whose latent heads are required (others return None)."""
         z_vector_list = []
+        levels = stack.encoder_forward(self, input)          # all level outputs through the linked stack, or None
         for i in range(len(self.layers)):
-            input = self._level(i, input)
+            input = levels[i] if levels is not None else self._level(i, input)
             if needed is not None and i not in needed:
                 z_vector_list.append(None)
                 continue
@@ -178,6 +179,9 @@ class Decoder(nn.Module):
     def conv_plans(self):
         if self.hp['extra_conv']:
             return []
+        last = stack._last_plans.get(self)                  # the linked stack's plans once it has run (stack.decoder_forward)
+        if last is not None and stack._enabled and ops._conv_impl != ops.IMPL_SIMT:
+            return [(p, c.weight) for p, c in zip(last, self.convs)]
         return [(c.plan(**self._fused_kwargs(i)), c.weight) for i, c in enumerate(self.convs)]
 
     def _level(self, i, x):
@@ -205,6 +209,11 @@ class Decoder(nn.Module):
             return f.view(z.size(0), -1, self.timestep_list[z_idx])
 
         x = feats(0)
+        nl = self.hp['num_layers']
+        if nl > 1 and len(self.layers) == nl:
+            out = stack.decoder_forward(self, x, feats(nl - 1))
+            if out is not None:
+                return out
         for i in range(len(self.layers)):
             if i == self.hp['num_layers'] - 1 and i != 0:
                 bs, _, t = x.size()

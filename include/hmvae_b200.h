@@ -96,6 +96,59 @@ int hmvae_conv_fprop_tc(const hmvae_conv_plan* plan, const float* x, const float
                         int batch, int t_in, void* workspace, long workspace_bytes, void* stream);
 int hmvae_conv_dgrad_tc(const hmvae_conv_plan* plan, const float* dy, const float* y, const float* wp_dgrad, float* dxin,
                         int batch, int t_in, void* workspace, long workspace_bytes, void* stream);
+/* ---- stack-level path: the three phases of a tensor-core conv as separate calls, and the inter-layer link kernel.
+ *
+ * hmvae_conv_tc_stage  : the staging pass only (padding / upsample / unpool gather, or zero insertion + LeakyReLU' for dgrad).
+ * hmvae_conv_tc_run    : the tcgen05 kernel only: staged tiles -> raw accumulator dump (split-K partials, no bias).
+ * hmvae_conv_tc_finish : dump -> result tensor (split-K sum, bias, LeakyReLU / reflect fold), as hmvae_conv_{fprop,dgrad}_tc do.
+ * hmvae_conv_tc_sizes  : bytes of the staging buffer and of the dump for (plan, mode, batch, t_in); returns 0 if unsupported.
+ * mode: 0 fprop, 1 dgrad.  hmvae_conv_{fprop,dgrad}_tc == stage + run + finish on one workspace. */
+int hmvae_conv_tc_sizes(const hmvae_conv_plan* plan, int batch, int t_in, int mode, long* stage_bytes, long* dump_bytes);
+int hmvae_conv_tc_stage(const hmvae_conv_plan* plan, int mode, const float* src, const float* yact, int batch, int t_in,
+                        void* stage_ws, void* stream);
+int hmvae_conv_tc_run(const hmvae_conv_plan* plan, int mode, const float* wp, int batch, int t_in, const void* stage_ws,
+                      void* dump_ws, void* stream);
+int hmvae_conv_tc_finish(const hmvae_conv_plan* plan, int mode, const void* dump_ws, const float* bias, float* dst, int batch,
+                         int t_in, void* stream);
+
+/* hmvae_conv_link: ONE kernel for everything between two convs of a stack (replaces finish of the producer, SkeletonPool +
+ * LeakyReLU / nn.Upsample + SkeletonUnpool + the last decoder level's per-edge concat -- seq_two_hier_sa_vae.py:120-130,
+ * 233-258, 278-288 -- or their adjoints, and the staging pass of the consumer).  It reads the producer's dump, writes the
+ * boundary tensor S (NCW, [batch, s_joints * s_cpj, s_t]) and, when `cons` is given, the consumer's staged tiles.
+ *   kind 0 (forward)  : S = act(mean over pool members of (conv_P + bias)); `aux` [batch, s_joints*(ojs_P - co_P), s_t] fills the
+ *                       remaining channels of every joint when the producer plan has out_joint_stride > co (concat).
+ *                       pool_off / pool_idx: HOST CSR pooled edge -> producer joints (NULL: identity), pool_joints rows.
+ *                       cons = the next conv (its upsample / unpool / padding are applied on the fly), mode fprop.
+ *   kind 1 (backward, decoder side): producer = dgrad of conv P; S = gradient of P's source tensor (adjoint of P's upsample /
+ *                       unpool), [batch, src_joints_P * ci_P, T_src].  cons = the previous conv (mode dgrad); yact_c = its
+ *                       activated output in the layout of S when it fuses LeakyReLU.
+ *   kind 2 (backward, encoder side): producer = dgrad of conv P whose input is pool(+LeakyReLU) of conv C's output;
+ *                       S = gradient of C's raw output = pool^T(lrelu'(sact) * (dgrad_P + add)); sact / add: [batch, J_P*ci_P, T_P].
+ * stage_ws: the consumer's staging buffer -- PERSISTENT and ZERO-INITIALISED by the caller (hmvae_conv_tc_sizes bytes): the kernel
+ * writes only real values, padding rows / channels and zero-inserted positions must stay 0.
+ * hmvae_conv_link_supported: 1 if the descriptor's geometry can take this path (buffers may be NULL). */
+typedef struct {
+  int kind, batch;
+  const hmvae_conv_plan* prod;
+  int prod_t;                 /* t_in of the producer conv */
+  const hmvae_conv_plan* cons;
+  int cons_t;                 /* t_in of the consumer conv */
+  int act;
+  int pool_joints;
+  const int* pool_off;
+  const int* pool_idx;
+  const float* dump;
+  const float* bias;
+  const float* aux;
+  const float* add;
+  const float* sact;
+  const float* yact_c;
+  float* s_out;
+  void* stage_ws;
+} hmvae_conv_link_desc;
+int hmvae_conv_link_supported(const hmvae_conv_link_desc* desc);
+int hmvae_conv_link(const hmvae_conv_link_desc* desc, void* stream);
+
 /* Debug aid (tools/tc_phases.py): device buffer (8 x uint64 per CTA) that receives %globaltimer stamps from the following
  * hmvae_conv_{fprop,dgrad}_tc launches; NULL switches it off. */
 int hmvae_conv_tc_debug(void* buf);

@@ -707,3 +707,43 @@ def test_latent_optimisation_vs_reference_golden(impl, graph, tol, smpl):
         d = (moved[k].detach() - p.detach()).cpu()
         refd = g[f"dec_delta/{k}"]
         np.testing.assert_allclose(float(d.abs().sum()), refd[1], rtol=max(20 * tol, 2e-2), atol=1e-7, err_msg=k)
+
+
+# ------------------------------------------------------------------------------------------------ linked stack path
+@pytest.mark.parametrize("tag,hp,bs,iters", [("len64", HP64, 32, 0), ("len64-late", HP64, 5, 50001), ("len8", HP8, 8, 0), ("len8-late", HP8, 3, 20001)])
+def test_stack_path_matches_per_layer_path(tag, hp, bs, iters, smpl):
+    """The linked stack (hmvae_conv_link between the tcgen05 convs: stack.py) against the per-layer path on the same model,
+    inputs and epsilon: losses, every parameter gradient and the test() outputs.  Both round to TF32 at the same points, so the
+    two agree far more tightly than either does with the fp32 oracle (differences: fma order in pool / upsample)."""
+    from hm_vae_b200 import stack
+    parents, off = smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])
+    ora = O.HMVAEOracle(hp, parents, off).init(seed=0)
+    model = _load(TwoHierSAVAEModel(dict(hp), device=DEV), ora)
+    batch = O.synthetic_batch(bs, hp["train_seq_len"], parents, off, seed=77)
+    eps = O.draw_eps(ora, bs, seed=78)
+    data = (batch["seq_rot_6d"], batch["seq_rot_mat"])
+    out = {}
+    try:
+        for on in (False, True):
+            stack.set_enabled(on)
+            for p in model.parameters():
+                p.grad = None
+            n0 = ops._lib.launch_count()
+            res = model(data, hp, iters, eps_list=eps)
+            torch.cuda.synchronize()
+            launches = ops._lib.launch_count() - n0
+            sz = [torch.randn(bs, len(ora.levels[i]["pooling_list"]), hp["shallow_latent_d"] if i == 0 else hp["latent_d"],
+                              generator=torch.Generator().manual_seed(5)) for i in range(4)]
+            _, mean, samp, _ = model.test(data, dict(hp, random_root_rot_flag=False), 0, sampled_z_list=sz)
+            out[on] = dict(losses=[float(r) for r in res[:5]], launches=launches, mean=mean.cpu(), samp=samp.cpu(),
+                           grads={k: (p.grad.detach().cpu().clone() if p.grad is not None else None) for k, p in model.named_parameters()})
+    finally:
+        stack.set_enabled(True)
+    assert out[True]["launches"] < out[False]["launches"], (out[True]["launches"], out[False]["launches"])
+    np.testing.assert_allclose(out[True]["losses"], out[False]["losses"], rtol=2e-5)
+    assert rel_l2(out[True]["mean"], out[False]["mean"]) < 1e-4 and rel_l2(out[True]["samp"], out[False]["samp"]) < 1e-4
+    for k, g0 in out[False]["grads"].items():
+        g1 = out[True]["grads"][k]
+        assert (g0 is None) == (g1 is None), k
+        if g0 is not None and float(g0.abs().max()) > 0:
+            assert rel_l2(g1, g0) < 2e-3, (k, rel_l2(g1, g0))
