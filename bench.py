@@ -279,11 +279,36 @@ class KernelTimer:
     CONV = {"fprop": ("hmvae_conv_fprop", "hmvae_conv_fprop_tc"), "dgrad": ("hmvae_conv_dgrad", "hmvae_conv_dgrad_tc"),
             "wgrad": ("hmvae_conv_wgrad", "hmvae_conv_wgrad_tc")}
 
+    # the linked stack path (hm_vae_b200/stack.py) issues the phases of a conv separately: classified by their mode / kind argument
+    STACK = ("hmvae_conv_tc_stage", "hmvae_conv_tc_run", "hmvae_conv_link")
+
     def __init__(self, lib, repeat=1):
         """repeat > 1: every conv compute entry point is issued `repeat` times back to back between its two events (the
         calls are idempotent), so that the launch queue is full and the event pair measures device time, not host gaps."""
         self.lib, self.records, self.orig, self.repeat = lib, [], {}, repeat
-        self.conv_names = {n for v in self.CONV.values() for n in v}
+        self.conv_names = {n for v in self.CONV.values() for n in v} | set(self.STACK)
+
+    @classmethod
+    def klass(cls, name, a):
+        """conv class of one recorded call: 'fprop' / 'dgrad' / 'wgrad' or None."""
+        for c, names in cls.CONV.items():
+            if name in names:
+                return c
+        if name in ("hmvae_conv_tc_stage", "hmvae_conv_tc_run"):
+            return "fprop" if int(a[1]) == 0 else "dgrad"
+        if name == "hmvae_conv_link":
+            return "fprop" if int(a[0]._obj.kind) == 0 else "dgrad"
+        return None
+
+    def class_ms(self):
+        """device ms per conv class over all recorded calls (stage + tensor-core kernel + finish / link)."""
+        torch.cuda.synchronize()
+        out = {c: 0.0 for c in self.CONV}
+        for name, a, e0, e1, rep in self.records:
+            c = self.klass(name, a)
+            if c is not None:
+                out[c] += e0.elapsed_time(e1) / rep
+        return out
 
     def __enter__(self):
         from hm_vae_b200 import _lib
@@ -329,9 +354,15 @@ class KernelTimer:
         for name, a, e0, e1, rep in self.records:
             if not name.startswith("hmvae_conv_") or name in ("hmvae_conv_tc_supported", "hmvae_conv_tc_workspace", "hmvae_conv_packed_size"):
                 continue
-            key = a[0].value if hasattr(a[0], "value") else a[0]
+            if name == "hmvae_conv_link":
+                key = a[0]._obj.prod                    # attributed to the producer conv of the boundary
+            else:
+                key = a[0].value if hasattr(a[0], "value") else a[0]
             idx = order.setdefault(key, len(order))
-            k = "%s[L%d]" % (name.replace("hmvae_conv_", ""), idx)
+            label = name.replace("hmvae_conv_", "")
+            if name in self.STACK:
+                label = "%s_%s" % (self.klass(name, a), label)
+            k = "%s[L%d]" % (label, idx)
             out[k] = out.get(k, 0.0) + e0.elapsed_time(e1) / rep / steps
         return {k: round(v * 1e3, 1) for k, v in sorted(out.items())}
 
@@ -381,7 +412,7 @@ def inference_leg(model, hp, dev, pk, batch=512, iters=10):
         for _ in range(2):
             model.test((d6, dm), hp, 0, sampled_z_list=zs)
     summ = kt.summary()
-    conv_ms = sum(summ.get(n, dict(ms=0.0))["ms"] for n in KernelTimer.CONV["fprop"]) / 2
+    conv_ms = kt.class_ms()["fprop"] / 2
     fl = conv_flops(model, batch, enc_passes=1, dec_passes=2)
     tf = fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
     return {"workload": "configs/len_64_test_interpolation.yaml test() path, B=%d, no grad, eager" % batch, "ms_per_call": ms,
@@ -580,7 +611,7 @@ def run_b200(args, hp):
     line = None
     if rank == 0:
         summ, summ8 = kt.summary(), kt8.summary()
-        cls_ms = {c: sum(summ8.get(n, dict(ms=0.0))["ms"] for n in names) / prof_steps for c, names in KernelTimer.CONV.items()}
+        cls_ms = {c: v / prof_steps for c, v in kt8.class_ms().items()}
         fl_fwd = conv_flops_per_step(model, bs)
         top = max(cls_ms, key=lambda k: cls_ms[k])
         top_ms = cls_ms[top]

@@ -720,11 +720,20 @@ int conv_tc_run(const hmvae_conv_plan* plan, int mode, const float* wp, int B, i
   if (!stage_ws || !dump_ws || !aligned16(stage_ws) || !aligned16(dump_ws) || !aligned16(wp))
     return fail_arg("conv (tcgen05): workspace / packed weights must be 16-byte aligned");
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  static thread_local size_t smem_set = 0;      // the attribute is sticky: raise it only when a larger ring shows up
-  if (smem > smem_set) {
-    HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  // the limit is a per-function permission, sticky and process-wide (forward and autograd-engine threads both launch): raise it
+  // once to the device maximum (opt-in limit minus the kernel's static shared memory) instead of per launch
+  static std::atomic<long> smem_max{0};
+  if (smem_max.load(std::memory_order_acquire) == 0) {
+    int dev = 0, optin = 0;
+    cudaFuncAttributes fa;
+    HMVAE_CUDA(cudaGetDevice(&dev));
+    HMVAE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    HMVAE_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel));
+    const long lim = (long)optin - (long)fa.sharedSizeBytes;
+    HMVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+    smem_max.store(lim, std::memory_order_release);
   }
+  if ((long)smem > smem_max.load(std::memory_order_acquire)) return fail_arg("conv (tcgen05): stage ring exceeds the shared memory of an SM");
   dim3 grid(p.mtiles, p.groups, p.splits);
   launch_pdl<true>(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, p, reinterpret_cast<const unsigned char*>(stage_ws), wp,
                    (const float*)nullptr, reinterpret_cast<float*>(dump_ws));

@@ -579,7 +579,20 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
   const size_t epi = (size_t)128 * (16 * p.Lmax + 1) * 4;       // the epilogue's transpose tile reuses the stage buffers
   if (epi > smem) smem = epi;
   smem += 1024;
-  HMVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the limit is a per-function permission, sticky and process-wide (forward and autograd-engine threads both launch): raise it
+  // once to the device maximum (opt-in limit minus the kernel's static shared memory) instead of per launch
+  static std::atomic<long> smem_max{0};
+  if (smem_max.load(std::memory_order_acquire) == 0) {
+    int dev = 0, optin = 0;
+    cudaFuncAttributes fa;
+    HMVAE_CUDA(cudaGetDevice(&dev));
+    HMVAE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    HMVAE_CUDA(cudaFuncGetAttributes(&fa, conv_wgrad_tc_kernel));
+    const long lim = (long)optin - (long)fa.sharedSizeBytes;
+    HMVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+    smem_max.store(lim, std::memory_order_release);
+  }
+  if ((long)smem > smem_max.load(std::memory_order_acquire)) return fail_arg("conv_wgrad (tcgen05): stage ring exceeds the shared memory of an SM");
   float* part = reinterpret_cast<float*>(xw + wg_x_bytes(p));
   dim3 grid(p.nitems, p.psplits);
   launch_pdl<true>(conv_wgrad_tc_kernel, grid, dim3(WG_THREADS), smem, st, p, (const unsigned char*)dyw, (const unsigned char*)xw,
