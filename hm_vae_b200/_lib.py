@@ -71,6 +71,12 @@ class ConvLinkDesc(Structure):
                 ("yact_c", c_void_p), ("s_out", c_void_p), ("stage_ws", c_void_p)]
 
 
+class HeadLevel(Structure):
+    _fields_ = [("rows", c_int), ("features", c_int), ("d", c_int), ("kl_scale", c_float), ("x", c_void_p), ("enc_w", c_void_p),
+                ("enc_b", c_void_p), ("eps", c_void_p), ("dec_w", c_void_p), ("dec_b", c_void_p), ("dist", c_void_p), ("z", c_void_p),
+                ("feat", c_void_p), ("kl_acc", c_void_p), ("gfeat", c_void_p), ("gdist", c_void_p), ("gx", c_void_p)]
+
+
 class RegTensor(Structure):
     _fields_ = [("p", c_void_p), ("p0", c_void_p), ("g", c_void_p), ("numel", c_long), ("accumulate", c_int)]
 
@@ -130,6 +136,8 @@ _SIGS = {
     "hmvae_recon_fwdbwd": (c_int, [P, c_int, P, P, P, IP, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P]),
     "hmvae_recon_masked_fwdbwd": (c_int, [P, c_int, P, P, P, P, IP, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P, P]),
     "hmvae_l2_reg_fwdbwd": (c_int, [POINTER(RegTensor), c_int, c_float, P, P]),
+    "hmvae_latent_heads_fwd": (c_int, [POINTER(HeadLevel), c_int, P]),
+    "hmvae_latent_heads_bwd": (c_int, [POINTER(HeadLevel), c_int, P]),
     "hmvae_linear_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_linear_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "hmvae_loss_finalize": (c_int, [P, P, POINTER(c_float), POINTER(c_float), POINTER(c_float), c_int, P]),

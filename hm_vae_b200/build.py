@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libhmvae_b200.so")
-SOURCES = ["conv_api.cu", "conv_simt.cu", "conv_tc.cu", "conv_link.cu", "conv_wgrad_tc.cu", "fk.cu", "elem.cu", "recon.cu", "linear.cu", "dp.cu", "batch.cu"]
+SOURCES = ["conv_api.cu", "conv_simt.cu", "conv_tc.cu", "conv_link.cu", "conv_wgrad_tc.cu", "fk.cu", "elem.cu", "recon.cu", "linear.cu", "heads.cu", "dp.cu", "batch.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 

@@ -26,12 +26,13 @@
 
 namespace hmvae {
 
-constexpr int LK_CH = 4;          // S time steps per thread
+constexpr int LK_CH = 2;          // S time steps per item
 constexpr int LK_MAXJ = 64;
 
 struct LinkArgs {
   TcArgs P, C;                    // producer geometry (dump layout) / consumer geometry (staging layout); has_c == 0: no consumer
   int kind, has_c;
+  int zg;                         // lanes per item: the split-K partials of an item are summed by zg lanes (power of two <= 8)
   int ES, cs, cp, TS;             // S: joints, channels per joint, channels per joint that come from the dump, time steps
   int act;                        // kind 0: LeakyReLU on S; kind 2: multiply by LeakyReLU'(sact)
   int EP;                         // kind 2: joints of `add` / `sact` (= producer input joints)
@@ -54,29 +55,6 @@ __device__ __forceinline__ float4 f4_axpy(float s, float4 a, float4 b) {       /
   return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w));
 }
 
-// sum over the split-K partial dumps of one accumulator row, 4 consecutive columns (same order as conv_tc_finish_kernel)
-__device__ __forceinline__ float4 lk_dump4(const TcArgs& P, const float4* __restrict__ dump, int mt, int g, int row, int col4) {
-  const int dc4 = P.dcols >> 2;
-  const size_t zstride = (size_t)P.mtiles * P.groups * 128 * dc4;
-  const float4* d = dump + (((size_t)mt * P.groups + g) * 128 + row) * dc4 + col4;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z = 0; z < P.splits; ++z) v = f4_add(v, d[z * zstride]);
-  return v;
-}
-
-// gradient w.r.t. the producer conv's (virtual) input: joint n, channels 4q.., sequence b, step u -- reflect-padding adjoint folded
-__device__ __forceinline__ float4 lk_dgrad4(const TcArgs& P, const float4* __restrict__ dump, int b, int n, int q, int u) {
-  const ConvArgs& a = P.a;
-  const int mt = b / P.Bt, bl = b - mt * P.Bt;
-  const int g = n / P.GJ, col4 = ((n % P.GJ) * P.n_pad >> 2) + q;
-  float4 v = lk_dump4(P, dump, mt, g, (u + a.p) * P.Bt + bl, col4);
-  if (a.pad_mode == 1) {
-    if (u >= 1 && u <= a.p) v = f4_add(v, lk_dump4(P, dump, mt, g, (a.p - u) * P.Bt + bl, col4));
-    if (u <= P.T - 2 && u >= P.T - 1 - a.p) v = f4_add(v, lk_dump4(P, dump, mt, g, (a.p + 2 * (P.T - 1) - u) * P.Bt + bl, col4));
-  }
-  return v;
-}
-
 __device__ __forceinline__ float4 lk_tf32(float4 v) {
   return make_float4(__uint_as_float(to_tf32(v.x)), __uint_as_float(to_tf32(v.y)), __uint_as_float(to_tf32(v.z)),
                      __uint_as_float(to_tf32(v.w)));
@@ -89,21 +67,95 @@ __device__ __forceinline__ size_t lk_stage_index(const TcArgs& C, int mt, int n,
   return ((((size_t)mt * C.a.J + n) * (nq / qpb) + cb) * qpb + h) * C.rows_alloc + row;
 }
 
-__global__ void __launch_bounds__(128) conv_link_kernel(const __grid_constant__ LinkArgs L) {
+constexpr int LK_MAXK = 2 * LK_CH + 2;      // dump rows one thread accumulates side by side (kind 1 with upsample: 2*CH + 2)
+
+// acc[k] += sum over THIS LANE'S splits z = zl, zl + ZG, ... of dump[z][mt][g][row[k]][col4], for the k with row[k] >= 0.
+// The LK_MAXK loads of one split are independent and issued back to back, and the splits of one item are spread over ZG lanes
+// (an item at B=32 has up to 21 split-K partials x 2 pool members x 3 reflect folds: walked by one thread that is a ~10 us
+// dependent-latency chain; measured 20-30 us per link before this).
+__device__ __forceinline__ void lk_accum(const TcArgs& P, const float4* __restrict__ dump, int mt, int g, int col4, int zl, int ZG,
+                                         const int (&row)[LK_MAXK], float4 (&acc)[LK_MAXK]) {
+  const int dc4 = P.dcols >> 2;
+  const size_t zstride = (size_t)P.mtiles * P.groups * 128 * dc4;
+  const float4* d = dump + ((size_t)mt * P.groups + g) * 128 * dc4 + col4;
+#pragma unroll 2
+  for (int z = zl; z < P.splits; z += ZG) {
+    float4 t[LK_MAXK];
+#pragma unroll
+    for (int k = 0; k < LK_MAXK; ++k)
+      t[k] = row[k] >= 0 ? d[(size_t)z * zstride + (size_t)row[k] * dc4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < LK_MAXK; ++k) acc[k] = f4_add(acc[k], t[k]);
+  }
+}
+
+// gradient w.r.t. the producer conv's (virtual) input, joint n, channel group q, steps u0 .. u0 + nk - 1 (reflect-padding adjoint
+// folded in): G[k] += (this lane's share of the splits)
+__device__ __forceinline__ void lk_dgrad_rows(const TcArgs& P, const float4* __restrict__ dump, int b, int n, int q, int u0, int nk,
+                                              int zl, int ZG, float4 (&G)[LK_MAXK]) {
+  const ConvArgs& a = P.a;
+  const int mt = b / P.Bt, bl = b - mt * P.Bt;
+  const int g = n / P.GJ, col4 = ((n % P.GJ) * P.n_pad >> 2) + q;
+  int row[LK_MAXK];
+#pragma unroll
+  for (int k = 0; k < LK_MAXK; ++k) {
+    const int u = u0 + k;
+    row[k] = (k < nk && u >= 0 && u < P.T) ? (u + a.p) * P.Bt + bl : -1;
+  }
+  lk_accum(P, dump, mt, g, col4, zl, ZG, row, G);
+  if (a.pad_mode == 1) {
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < LK_MAXK; ++k) {
+      const int u = u0 + k;
+      row[k] = (k < nk && u >= 1 && u <= a.p && u < P.T) ? (a.p - u) * P.Bt + bl : -1;
+      any |= row[k] >= 0;
+    }
+    if (any) lk_accum(P, dump, mt, g, col4, zl, ZG, row, G);
+    any = false;
+#pragma unroll
+    for (int k = 0; k < LK_MAXK; ++k) {
+      const int u = u0 + k;
+      row[k] = (k < nk && u >= 0 && u <= P.T - 2 && u >= P.T - 1 - a.p) ? (a.p + 2 * (P.T - 1) - u) * P.Bt + bl : -1;
+      any |= row[k] >= 0;
+    }
+    if (any) lk_accum(P, dump, mt, g, col4, zl, ZG, row, G);
+  }
+}
+
+// butterfly sum over the ZG lanes of an item (fixed order: deterministic); every lane ends up with the total
+__device__ __forceinline__ void lk_reduce(float4 (&acc)[LK_MAXK], int ZG, unsigned mask) {
+  for (int o = ZG >> 1; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < LK_MAXK; ++k) {
+      acc[k].x += __shfl_xor_sync(mask, acc[k].x, o);
+      acc[k].y += __shfl_xor_sync(mask, acc[k].y, o);
+      acc[k].z += __shfl_xor_sync(mask, acc[k].z, o);
+      acc[k].w += __shfl_xor_sync(mask, acc[k].w, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 3) conv_link_kernel(const __grid_constant__ LinkArgs L) {
   pdl_trigger();
   pdl_wait();
   const TcArgs& P = L.P;
   const TcArgs& C = L.C;
+  const int ZG = L.zg;                                   // lanes per item (power of two <= 8)
   const int nq = (L.cs + 3) >> 2;
   const int nch = (L.TS + LK_CH - 1) / LK_CH;
   const long total = (long)P.B * L.ES * nq * nch;
-  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long)gridDim.x * blockDim.x) {
-    // channel group fastest: neighbouring threads read neighbouring dump columns and write neighbouring staged chunks
-    const int q = (int)(it % nq);
-    long r = it / nq;
-    const int e = (int)(r % L.ES); r /= L.ES;
-    const int ch = (int)(r % nch);
-    const int b = (int)(r / nch);
+  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = (int)(gtid & (ZG - 1));
+  const unsigned mask = (ZG == 32) ? 0xffffffffu : (((1u << ZG) - 1u) << ((threadIdx.x & 31) & ~(ZG - 1)));
+  for (long it = gtid / ZG; it < total; it += ((long)gridDim.x * blockDim.x) / ZG) {
+    // time chunk fastest: the lanes of a warp write consecutive steps of the same channel rows of S (coalesced NCW stores; with
+    // the channel group fastest every 8-byte store was its own sector: 80 us for the 19 MB of the last decoder level at B=512)
+    const int ch = (int)(it % nch);
+    long r = it / nch;
+    const int q = (int)(r % nq); r /= nq;
+    const int e = (int)(r % L.ES);
+    const int b = (int)(r / L.ES);
     const int i0 = ch * LK_CH;
     const int i1 = (i0 + LK_CH < L.TS) ? i0 + LK_CH : L.TS;
     const int c0 = q << 2;
@@ -113,51 +165,79 @@ __global__ void __launch_bounds__(128) conv_link_kernel(const __grid_constant__ 
     for (int k = 0; k < LK_CH + 2; ++k) sv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int klo = (up_f && i0 > 0) ? 0 : 1, khi = (up_f && i1 < L.TS) ? (i1 - i0 + 2) : (i1 - i0 + 1);
     const float scale = L.m_scale[e];
-    for (int k = klo; k < khi; ++k) {
-      const int t = i0 - 1 + k;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (L.kind == 0) {
-        if (c0 < L.cp) {
-          const int mt = b / P.Bt, row = t * P.Bt + (b - mt * P.Bt);
-          for (int m = L.m_off[e]; m < L.m_off[e + 1]; ++m) {
-            const int j = L.m_idx[m];
-            float4 d = lk_dump4(P, L.dump, mt, j / P.GJ, row, ((j % P.GJ) * P.n_pad >> 2) + q);
-            if (L.bias) {
-              const float* bp = L.bias + j * P.a.co + c0;
-              d.x += bp[0];
-              if (c0 + 1 < P.a.co) d.y += bp[1];
-              if (c0 + 2 < P.a.co) d.z += bp[2];
-              if (c0 + 3 < P.a.co) d.w += bp[3];
-            }
-            v = f4_axpy(scale, d, v);
+    float4 acc[LK_MAXK];
+#pragma unroll
+    for (int k = 0; k < LK_MAXK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (L.kind == 0) {
+      if (c0 < L.cp) {
+        const int mt = b / P.Bt, bl = b - mt * P.Bt;
+        int row[LK_MAXK];
+#pragma unroll
+        for (int k = 0; k < LK_MAXK; ++k) row[k] = (k >= klo && k < khi) ? (i0 - 1 + k) * P.Bt + bl : -1;
+        float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = L.m_off[e]; m < L.m_off[e + 1]; ++m) {
+          const int j = L.m_idx[m];
+          lk_accum(P, L.dump, mt, j / P.GJ, ((j % P.GJ) * P.n_pad >> 2) + q, zl, ZG, row, acc);
+          if (L.bias) {
+            const float* bp = L.bias + j * P.a.co + c0;
+            bsum.x += bp[0];
+            if (c0 + 1 < P.a.co) bsum.y += bp[1];
+            if (c0 + 2 < P.a.co) bsum.z += bp[2];
+            if (c0 + 3 < P.a.co) bsum.w += bp[3];
           }
+        }
+        lk_reduce(acc, ZG, mask);
+#pragma unroll
+        for (int k = 0; k < LK_CH + 2; ++k) {
+          float4 v = f4_scale(f4_add(acc[k], bsum), scale);          // mean over the pool members of (conv + bias)
           if (L.act) { v.x = lrelu_f(v.x, 0.2f); v.y = lrelu_f(v.y, 0.2f); v.z = lrelu_f(v.z, 0.2f); v.w = lrelu_f(v.w, 0.2f); }
           if (c0 + 1 >= L.cp) v.y = 0.f;
           if (c0 + 2 >= L.cp) v.z = 0.f;
           if (c0 + 3 >= L.cp) v.w = 0.f;
-        } else {
-          const int ca = L.cs - L.cp;
-          const float* ap = L.aux + (((size_t)b * L.ES + e) * ca + (c0 - L.cp)) * L.TS + t;
-          v.x = ap[0];
+          sv[k] = v;
+        }
+      } else {
+        const int ca = L.cs - L.cp;
+#pragma unroll
+        for (int k = 0; k < LK_CH + 2; ++k) {
+          if (k < klo || k >= khi) continue;
+          const float* ap = L.aux + (((size_t)b * L.ES + e) * ca + (c0 - L.cp)) * L.TS + (i0 - 1 + k);
+          float4 v = make_float4(ap[0], 0.f, 0.f, 0.f);
           if (c0 + 1 < L.cs) v.y = ap[(size_t)L.TS];
           if (c0 + 2 < L.cs) v.z = ap[2 * (size_t)L.TS];
           if (c0 + 3 < L.cs) v.w = ap[3 * (size_t)L.TS];
+          sv[k] = v;
         }
-      } else if (L.kind == 1) {
-        for (int m = L.m_off[e]; m < L.m_off[e + 1]; ++m) {
-          const int n = L.m_idx[m];
-          if (P.a.upsample) {
-            float4 g = f4_scale(f4_add(lk_dgrad4(P, L.dump, b, n, q, 2 * t), lk_dgrad4(P, L.dump, b, n, q, 2 * t + 1)), 0.75f);
-            g = f4_axpy(0.25f, lk_dgrad4(P, L.dump, b, n, q, t + 1 < L.TS ? 2 * t + 2 : 2 * t + 1), g);
-            g = f4_axpy(0.25f, lk_dgrad4(P, L.dump, b, n, q, t > 0 ? 2 * t - 1 : 0), g);
-            v = f4_add(v, g);
-          } else {
-            v = f4_add(v, lk_dgrad4(P, L.dump, b, n, q, t));
-          }
+      }
+    } else if (L.kind == 1) {
+      const bool up = P.a.upsample != 0;
+      const int u0 = up ? 2 * i0 - 1 : i0;                           // acc[k] = gradient at conv-input step u0 + k
+      const int nk = up ? 2 * (i1 - i0) + 2 : (i1 - i0);
+      for (int m = L.m_off[e]; m < L.m_off[e + 1]; ++m) lk_dgrad_rows(P, L.dump, b, L.m_idx[m], q, u0, nk, zl, ZG, acc);
+      lk_reduce(acc, ZG, mask);
+#pragma unroll
+      for (int kk = 0; kk < LK_CH; ++kk) {
+        const int t = i0 + kk;
+        if (t >= i1) break;
+        if (up) {
+          // upsample2^T: .75 (g[2t] + g[2t+1]) + .25 (t+1 < Ts ? g[2t+2] : g[2t+1]) + .25 (t > 0 ? g[2t-1] : g[0])
+          float4 v = f4_scale(f4_add(acc[2 * kk + 1], acc[2 * kk + 2]), 0.75f);
+          v = f4_axpy(0.25f, (t + 1 < L.TS) ? acc[2 * kk + 3] : acc[2 * kk + 2], v);
+          v = f4_axpy(0.25f, (t > 0) ? acc[2 * kk] : acc[2 * kk + 1], v);
+          sv[kk + 1] = v;
+        } else {
+          sv[kk + 1] = acc[kk];
         }
-      } else {
-        const int ep = L.m_idx[L.m_off[e]];                      // the pooled joint that S joint e was averaged into
-        v = lk_dgrad4(P, L.dump, b, ep, q, t);
+      }
+    } else {
+      const int ep = L.m_idx[L.m_off[e]];                        // the pooled joint that S joint e was averaged into
+      lk_dgrad_rows(P, L.dump, b, ep, q, i0, i1 - i0, zl, ZG, acc);
+      lk_reduce(acc, ZG, mask);
+#pragma unroll
+      for (int kk = 0; kk < LK_CH; ++kk) {
+        const int t = i0 + kk;
+        if (t >= i1) break;
+        float4 v = acc[kk];
         const size_t base = (((size_t)b * L.EP + ep) * L.cs + c0) * L.TS + t;
         if (L.add) {
           v.x += L.add[base];
@@ -171,30 +251,29 @@ __global__ void __launch_bounds__(128) conv_link_kernel(const __grid_constant__ 
           if (c0 + 2 < L.cs && !(L.sact[base + 2 * (size_t)L.TS] > 0.f)) v.z *= 0.2f;
           if (c0 + 3 < L.cs && !(L.sact[base + 3 * (size_t)L.TS] > 0.f)) v.w *= 0.2f;
         }
-        v = f4_scale(v, scale);
+        sv[kk + 1] = f4_scale(v, scale);
       }
-      sv[k] = v;
     }
-    // ---- the boundary tensor itself (NCW): 4 channel rows x (i1 - i0) consecutive steps
-    {
+    // ---- the boundary tensor itself (NCW): 4 channel rows x (i1 - i0) consecutive steps, written by lane 0 of the item
+    if (zl == 0) {
       float* sp = L.S + (((size_t)b * L.ES + e) * L.cs + c0) * L.TS + i0;
       const int len = i1 - i0;
-      const float rowv[4][LK_CH] = {{sv[1].x, sv[2].x, sv[3].x, sv[4].x}, {sv[1].y, sv[2].y, sv[3].y, sv[4].y},
-                                    {sv[1].z, sv[2].z, sv[3].z, sv[4].z}, {sv[1].w, sv[2].w, sv[3].w, sv[4].w}};
+      const float rowv[4][LK_CH] = {{sv[1].x, sv[2].x}, {sv[1].y, sv[2].y}, {sv[1].z, sv[2].z}, {sv[1].w, sv[2].w}};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c0 + c >= L.cs) break;
         float* rp = sp + (size_t)c * L.TS;
-        if (len == LK_CH && (L.TS & 3) == 0) {
-          *reinterpret_cast<float4*>(rp) = make_float4(rowv[c][0], rowv[c][1], rowv[c][2], rowv[c][3]);
+        if (len == LK_CH && (L.TS & 1) == 0) {
+          *reinterpret_cast<float2*>(rp) = make_float2(rowv[c][0], rowv[c][1]);
         } else {
           for (int k = 0; k < len; ++k) rp[k] = rowv[c][k];
         }
       }
     }
     if (!L.has_c) continue;
-    // ---- scatter into the consumer's staged tiles
+    // ---- scatter into the consumer's staged tiles; the (fan-out joint, step) pairs of an item are dealt round-robin to its lanes
     const int mtc = b / C.Bt, blc = b - mtc * C.Bt;
+    int turn = 0;
     if (L.kind == 0) {
       const ConvArgs& ca = C.a;
       const int Tc = C.T;
@@ -212,12 +291,16 @@ __global__ void __launch_bounds__(128) conv_link_kernel(const __grid_constant__ 
       };
       for (int f = L.f_off[e]; f < L.f_off[e + 1]; ++f) {
         const int n = L.f_idx[f];
-        for (int i = i0; i < i1; ++i) {
-          const float4 cur = sv[i - i0 + 1];
+#pragma unroll
+        for (int kk = 0; kk < LK_CH; ++kk) {
+          const int i = i0 + kk;
+          if (i >= i1) break;
+          if (((turn++) & (ZG - 1)) != zl) continue;
+          const float4 cur = sv[kk + 1];
           if (!ca.upsample) {
             put(n, i, cur);
           } else {
-            const float4 lo = (i > 0) ? sv[i - i0] : cur, hi = (i + 1 < L.TS) ? sv[i - i0 + 2] : cur;
+            const float4 lo = (i > 0) ? sv[kk] : cur, hi = (i + 1 < L.TS) ? sv[kk + 2] : cur;
             put(n, 2 * i, f4_axpy(0.75f, cur, f4_scale(lo, 0.25f)));
             put(n, 2 * i + 1, f4_axpy(0.75f, cur, f4_scale(hi, 0.25f)));
           }
@@ -229,8 +312,12 @@ __global__ void __launch_bounds__(128) conv_link_kernel(const __grid_constant__ 
       if (c0 >= ca.co) continue;
       for (int f = L.f_off[e]; f < L.f_off[e + 1]; ++f) {
         const int n = L.f_idx[f];
-        for (int i = i0; i < i1; ++i) {
-          float4 val = sv[i - i0 + 1];
+#pragma unroll
+        for (int kk = 0; kk < LK_CH; ++kk) {
+          const int i = i0 + kk;
+          if (i >= i1) break;
+          if (((turn++) & (ZG - 1)) != zl) continue;
+          float4 val = sv[kk + 1];
           if (ca.lrelu) {
             const size_t base = (((size_t)b * L.ES + e) * L.cs + c0) * L.TS + i;
             if (!(L.yact_c[base] > 0.f)) val.x *= 0.2f;
@@ -385,7 +472,13 @@ extern "C" int hmvae_conv_link(const hmvae_conv_link_desc* desc, void* stream) {
   }
   if (!aligned16(desc->dump) || !aligned16(desc->s_out) || (desc->cons && !aligned16(desc->stage_ws)))
     return fail_arg("conv_link: buffers must be 16-byte aligned");
-  const long total = (long)L.P.B * L.ES * ((L.cs + 3) / 4) * ((L.TS + LK_CH - 1) / LK_CH);
+  const long items = (long)L.P.B * L.ES * ((L.cs + 3) / 4) * ((L.TS + LK_CH - 1) / LK_CH);
+  // lanes per item: enough to cut the split-K walk to <= 2-3 partials per lane, but only while the grid stays small
+  int zg = 1;
+  const int zg_max = env_int("HMVAE_LINK_ZG", 8), per_lane = env_int("HMVAE_LINK_ZPER", 2);
+  while (zg < zg_max && zg * 2 * per_lane <= 2 * L.P.splits && items * zg * 2 <= (long)num_sms() * 2048) zg *= 2;
+  L.zg = zg;
+  const long total = items * zg;
   long blocks = (total + 127) / 128, cap = (long)num_sms() * 16;
   if (blocks < 1) blocks = 1;
   launch_pdl(conv_link_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(128), 0, (cudaStream_t)stream, L);

@@ -70,8 +70,16 @@ _overlap = {"on": False, "side": None, "pending": [], "allowed": True}
 def _side_stream():
     """The stream of the weight packing (forward) -- also side stream 0 of the weight gradients."""
     if _overlap["side"] is None:
-        _overlap["side"] = torch.cuda.Stream()
+        _overlap["side"] = torch.cuda.Stream(priority=0)
     return _overlap["side"]
+
+
+def main_stream_priority():
+    """Priority of the stream a training step is captured on (Trainer.enable_cuda_graph).  The forward / data-gradient chain is
+    the critical path of a step; weight gradients, weight packing and the optimiser run beside it on default-priority streams.
+    With a higher priority (HMVAE_MAIN_PRIORITY, default -1) the block scheduler serves the chain's CTAs first whenever both
+    have blocks pending (tools/timeline.py: dgrad kernels took 20-33 us next to the weight gradients, 13-23 us alone)."""
+    return int(os.environ.get("HMVAE_MAIN_PRIORITY", "-1"))
 
 
 def _wgrad_stream():
@@ -80,7 +88,7 @@ def _wgrad_stream():
     n = max(1, int(os.environ.get("HMVAE_WGRAD_STREAMS", "1")))
     pool = _overlap.setdefault("pool", [])
     while len(pool) < n:
-        pool.append(_side_stream() if not pool else torch.cuda.Stream())
+        pool.append(_side_stream() if not pool else torch.cuda.Stream(priority=0))
     _overlap["rr"] = (_overlap.get("rr", -1) + 1) % n
     s = pool[_overlap["rr"]]
     _overlap.setdefault("used", set()).add(s)
@@ -580,6 +588,103 @@ class _LatentFusedFn(Function):
 
 def latent_fused(dist, eps, d, kl_grad_scale, kl_acc):
     return _LatentFusedFn.apply(dist, eps, d, kl_grad_scale, kl_acc)
+
+
+class _HeadsFn(Function):
+    """Encoder head -> reparametrise (+ KL) -> decoder head for several hierarchy levels in ONE kernel per direction
+    (``hmvae_latent_heads_fwd / _bwd``).  ``levels``: list of dicts(d, kl_scale, kl_acc, detach); tensors per level, flattened:
+    (x [B, k, F], enc_w, enc_b, dec_w, dec_b, eps-or-None).  Returns the per-level decoder features [B, k, F] followed by the
+    per-level distributions [B, k, 2d] (outputs for inspection; non-differentiable).
+    ``detach``: the level's latent and KL are cut from the encoder (seq_two_hier_sa_vae.py:380-383): only its decoder head trains."""
+
+    @staticmethod
+    def forward(ctx, levels, *tensors):
+        n = len(levels)
+        arr = (_lib.HeadLevel * n)()
+        xs, feats, dists, zs, keep = [], [], [], [], []
+        for l, meta in enumerate(levels):
+            x, ew, eb, dw, db, eps = tensors[6 * l:6 * l + 6]
+            x = x.contiguous()
+            b, k, f = x.shape
+            rows, d = b * k, meta["d"]
+            dist = torch.empty((b, k, 2 * d), device=x.device, dtype=torch.float32)
+            z = torch.empty((rows, d), device=x.device, dtype=torch.float32)
+            feat = torch.empty((b, k, f), device=x.device, dtype=torch.float32)
+            ew, dw = ew.contiguous(), dw.contiguous()
+            h = arr[l]
+            h.rows, h.features, h.d, h.kl_scale = rows, f, d, 0.0
+            h.x, h.enc_w, h.enc_b, h.dec_w, h.dec_b = ptr(x), ptr(ew), ptr(eb), ptr(dw), ptr(db)
+            h.eps = ptr(eps.contiguous()) if eps is not None else None
+            h.dist, h.z, h.feat = ptr(dist), ptr(z), ptr(feat)
+            h.kl_acc = meta["kl_acc"].data_ptr() if meta.get("kl_acc") is not None else None
+            xs.append(x); feats.append(feat); dists.append(dist); zs.append(z); keep.extend([ew, dw, eps])
+        check(lib.hmvae_latent_heads_fwd(arr, n, stream()), "latent_heads_fwd")
+        ctx.levels = levels
+        ctx.bias_refs = [(tensors[6 * l + 2], tensors[6 * l + 4]) for l in range(n)]
+        ctx.save_for_backward(*xs, *dists, *zs, *[tensors[6 * l + 1] for l in range(n)], *[tensors[6 * l + 3] for l in range(n)],
+                              *[t if t is not None else xs[0].new_empty(0) for t in (tensors[6 * l + 5] for l in range(n))])
+        for t in dists:
+            ctx.mark_non_differentiable(t)
+        return tuple(feats) + tuple(dists)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        levels = ctx.levels
+        n = len(levels)
+        sv = ctx.saved_tensors
+        xs, dists, zs, ews, dws, epss = (sv[i * n:(i + 1) * n] for i in range(6))
+        gfeats = [g.contiguous() if g is not None else None for g in grads[:n]]
+        out = [None] * (1 + 6 * n)
+        live = [l for l in range(n) if gfeats[l] is not None]
+        prop = [l for l in live if not levels[l].get("detach", False)]        # levels whose gradient reaches the encoder
+        gdists = {}
+        if prop:
+            arr = (_lib.HeadLevel * len(prop))()
+            for i, l in enumerate(prop):
+                x, dist = xs[l], dists[l]
+                b, k, f = x.shape
+                d = levels[l]["d"]
+                gd = torch.empty_like(dist)
+                gx = torch.empty_like(x)
+                h = arr[i]
+                h.rows, h.features, h.d, h.kl_scale = b * k, f, d, float(levels[l]["kl_scale"])
+                h.enc_w, h.dec_w, h.dist = ptr(ews[l].contiguous()), ptr(dws[l].contiguous()), ptr(dist)
+                h.eps = ptr(epss[l]) if epss[l].numel() else None
+                h.gfeat, h.gdist, h.gx = ptr(gfeats[l]), ptr(gd), ptr(gx)
+                gdists[l] = gd
+                out[1 + 6 * l] = gx
+            check(lib.hmvae_latent_heads_bwd(arr, len(prop), stream()), "latent_heads_bwd")
+        # weight / bias gradients of the four small linears: generic kernels, on the side stream (they feed only the optimiser)
+        side = None
+        if _overlap["on"]:
+            side = _wgrad_stream()
+            side.wait_stream(torch.cuda.current_stream())
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            for l in live:
+                x, z, gf = xs[l], zs[l], gfeats[l]
+                b, k, f = x.shape
+                rows, d = b * k, levels[l]["d"]
+                eb, db = ctx.bias_refs[l]
+                if ctx.needs_input_grad[1 + 6 * l + 3]:            # decoder head: feat = z dec_w^T + dec_b
+                    gw = grad_buffer(dws[l])
+                    gb = grad_buffer(db.detach()) if db is not None else None
+                    check(lib.hmvae_linear_bwd(ptr(z), None, ptr(gf), None, ptr(gw), ptr(gb), rows, d, f, stream()), "linear_bwd(dw)")
+                    out[1 + 6 * l + 3], out[1 + 6 * l + 4] = gw, gb
+                if l in gdists and ctx.needs_input_grad[1 + 6 * l + 1]:      # encoder head: dist = x enc_w^T + enc_b
+                    gw = grad_buffer(ews[l])
+                    gb = grad_buffer(eb.detach()) if eb is not None else None
+                    check(lib.hmvae_linear_bwd(ptr(x), None, ptr(gdists[l]), None, ptr(gw), ptr(gb), rows, f, 2 * d, stream()), "linear_bwd(dw)")
+                    out[1 + 6 * l + 1], out[1 + 6 * l + 2] = gw, gb
+        if side is not None:
+            _overlap["pending"].extend(list(xs) + list(zs) + gfeats + list(gdists.values()))
+        return tuple(out)
+
+
+def latent_heads(levels, tensors):
+    """See _HeadsFn.  Returns (feats per level, dists per level)."""
+    res = _HeadsFn.apply(levels, *tensors)
+    n = len(levels)
+    return res[:n], res[n:]
 
 
 def loss_finalize(acc, out, scale, w, wk):

@@ -287,36 +287,55 @@ class TwoHierSAVAEModel(nn.Module):
         n = hp['num_layers']
         detach_shallow = iterations < hp['iteration_interval']
 
-        ops.prefetch_packs(self.enc.conv_plans() + self.dec.conv_plans())   # tf32 weight copies, on the side stream
-        x = ops.transpose_ct(seq_rot_6d)                            # bs X (24*6) X T   (input is [B, T, C])
-        _, z_vec_list = self.enc(x, needed={0, n - 1})
         k_edges = [len(p) for p in self.enc.pooling_list]
         lat = [self.shallow_latent_d] + [self.latent_d] * (n - 1)
-        eps = self._draw_eps([(bs * k_edges[i], lat[i]) for i in range(n)], dev, eps_list) if hp['kl_w'] != 0 else [None] * n
-
+        eps, eps_ready = [None] * n, None
+        if hp['kl_w'] != 0:
+            if eps_list is not None:
+                eps = self._draw_eps(None, dev, eps_list)
+            else:
+                # the four N(0,1) draws depend on nothing: issue them on the side stream, off the encoder's critical path
+                side, main = ops._side_stream(), torch.cuda.current_stream()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    eps = self._draw_eps([(bs * k_edges[i], lat[i]) for i in range(n)], dev, None)
+                    eps_ready = torch.cuda.Event()
+                    eps_ready.record()
+                for e in eps:
+                    e.record_stream(main)
+        ops.prefetch_packs(self.enc.conv_plans() + self.dec.conv_plans())   # tf32 weight copies, on the side stream
+        x = ops.transpose_ct(seq_rot_6d)                            # bs X (24*6) X T   (input is [B, T, C])
         # persistent accumulators: [sum sq 6d, sum sq rot, sum sq pos, unused, KL sum shallow, KL sum deep]; zeroed by finalize
         acc, res = self._loss_buffers(dev)
-        z_list = [None] * n
-        levels = (0, n - 1) if n > 1 else (0,)
-        for zi in levels:
-            dist = z_vec_list[zi]
-            deep = zi == n - 1
-            kl_w = hp['kl_w'] if deep else hp['shallow_kl_w']
-            slot = acc[5:6] if deep else acc[4:5]
-            if (not deep) and detach_shallow:
-                with torch.no_grad():
-                    z = ops.latent_fused(dist.detach(), eps[zi], lat[zi], 0.0, slot)
-            else:
-                z = ops.latent_fused(dist, eps[zi], lat[zi], kl_w / (bs * k_edges[zi]), slot)
-            z_list[zi] = z.view(bs, k_edges[zi], -1)
-
-        # Split backward (when a mid-backward callback is installed): the decoder runs on detached latents, so that its
-        # backward finishes -- and its optimiser / collective share can start -- before the encoder's backward begins.
         split = self.mid_backward is not None and not validation_flag
-        z_enc = list(z_list)
-        if split:
-            z_list = [z.detach().requires_grad_(z.requires_grad) if z is not None else None for z in z_list]
-        out = self.dec(z_list)                                      # bs X (24*6) X T
+        out = self._fused_bottleneck(x, eps, eps_ready, acc, hp, detach_shallow, split) if n > 1 else None
+        fused = out is not None
+        if fused:
+            out, enc_outs, enc_cut = out
+        else:
+            _, z_vec_list = self.enc(x, needed={0, n - 1})
+            if eps_ready is not None:
+                torch.cuda.current_stream().wait_event(eps_ready)
+            z_list = [None] * n
+            levels = (0, n - 1) if n > 1 else (0,)
+            for zi in levels:
+                dist = z_vec_list[zi]
+                deep = zi == n - 1
+                kl_w = hp['kl_w'] if deep else hp['shallow_kl_w']
+                slot = acc[5:6] if deep else acc[4:5]
+                if (not deep) and detach_shallow:
+                    with torch.no_grad():
+                        z = ops.latent_fused(dist.detach(), eps[zi], lat[zi], 0.0, slot)
+                else:
+                    z = ops.latent_fused(dist, eps[zi], lat[zi], kl_w / (bs * k_edges[zi]), slot)
+                z_list[zi] = z.view(bs, k_edges[zi], -1)
+
+            # Split backward (when a mid-backward callback is installed): the decoder runs on detached latents, so that its
+            # backward finishes -- and its optimiser / collective share can start -- before the encoder's backward begins.
+            z_enc = list(z_list)
+            if split:
+                z_list = [z.detach().requires_grad_(z.requires_grad) if z is not None else None for z in z_list]
+            out = self.dec(z_list)                                      # bs X (24*6) X T
         fk_off = self.fk_layer.positions[0].contiguous()
         dx6 = ops.recon_fwdbwd(out.detach(), True, seq_rot_6d, seq_rot_mat, fk_off, self._parents, hp['rec_6d_w'],
                                hp['rec_rot_w'], hp['rec_pose_w'], acc, want_grad=not validation_flag)
@@ -335,13 +354,53 @@ class TwoHierSAVAEModel(nn.Module):
         if not validation_flag:
             with ops.wgrad_overlap():
                 out.backward(dx6)
-                if split:
+                if split and fused:
+                    self.mid_backward()
+                    pairs = [(a, c.grad) for a, c in zip(enc_outs, enc_cut) if c.grad is not None]
+                    if pairs:
+                        torch.autograd.backward([a for a, _ in pairs], [g for _, g in pairs])
+                elif split:
                     self.mid_backward()
                     pairs = [(ze, zd.grad) for ze, zd in zip(z_enc, z_list) if ze is not None and ze.requires_grad and zd.grad is not None]
                     if pairs:
                         torch.autograd.backward([a for a, _ in pairs], [g for _, g in pairs])
 
         return l_total, l_kl, l_rec_6d, l_rec_rot_mat, l_rec_pose, zero, zero, zero, zero, l_kl_list
+
+    def _fused_bottleneck(self, x, eps, eps_ready, acc, hp, detach_shallow, split):
+        """Encoder stack -> both latent heads + reparametrisation + KL + both decoder heads in one kernel -> decoder stack (the
+        linked tensor-core path, stack.py).  Returns (decoder output, encoder outputs fed to the heads, their detached twins when
+        ``split``) or None when the linked path cannot run this geometry (caller takes the per-layer path)."""
+        from . import stack
+        n = hp['num_layers']
+        enc, dec = self.enc, self.dec
+        if len(dec.layers) != n or hp['extra_conv']:
+            return None
+        outs = stack.encoder_forward(enc, x)
+        if outs is None:
+            return None
+        bs = x.shape[0]
+        k_edges = [len(p) for p in enc.pooling_list]
+        if eps_ready is not None:
+            torch.cuda.current_stream().wait_event(eps_ready)
+        srcs = [outs[0], outs[n - 1]]                       # shallow (level 0) and deep (level n-1) features
+        cut = srcs
+        if split:                                            # decoder + heads backward first, then the optimiser's decoder share
+            cut = [t.detach().requires_grad_(True) for t in srcs]
+        d_sh, d_dp = self.shallow_latent_d, self.latent_d
+        metas = [dict(d=d_sh, kl_scale=hp['shallow_kl_w'] / (bs * k_edges[0]), kl_acc=acc[4:5], detach=bool(detach_shallow)),
+                 dict(d=d_dp, kl_scale=hp['kl_w'] / (bs * k_edges[n - 1]), kl_acc=acc[5:6], detach=False)]
+        he0, he3 = enc.latent_enc_layers[0], enc.latent_enc_layers[n - 1]
+        hd_sh, hd_dp = dec.latent_dec_layers[n - 1], dec.latent_dec_layers[0]      # decoder heads: index 0 takes the deep latent
+        tensors = [cut[0].view(bs, k_edges[0], -1), he0.weight, he0.bias, hd_sh.weight, hd_sh.bias, eps[0],
+                   cut[1].view(bs, k_edges[n - 1], -1), he3.weight, he3.bias, hd_dp.weight, hd_dp.bias, eps[n - 1]]
+        feats, _ = ops.latent_heads(metas, tensors)
+        feat_sh = feats[0].view(bs, -1, dec.timestep_list[n - 1])
+        feat_dp = feats[1].view(bs, -1, dec.timestep_list[0])
+        out = stack.decoder_forward(dec, feat_dp, feat_sh)
+        if out is None:
+            return None
+        return out, srcs, cut
 
     # ------------------------------------------------------------------ reference helpers kept for callers
     def reparametrize(self, pred_mean, pred_logvar):

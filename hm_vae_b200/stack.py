@@ -147,7 +147,8 @@ class _DecoderStackFn(Function):
         bounds = [feat0]                                     # bounds[i] = source tensor of conv i
         st, dump = _bufs(plans[0], 0, b, geo.t_in[0])
         check(lib.hmvae_conv_tc_stage(plans[0].handle, 0, ptr(feat0), None, b, geo.t_in[0], ptr(st), stream()), "conv_tc_stage")
-        packs = [_packed(plans[i], ws[i]) for i in range(n)]
+        packs = [None] * n                                   # each conv waits for ITS packed weights only (packing runs on the side stream)
+        packs[0] = _packed(plans[0], ws[0])
         check(lib.hmvae_conv_tc_run(plans[0].handle, 0, ptr(packs[0][0]), b, geo.t_in[0], ptr(st), ptr(dump), stream()), "conv_tc_run")
         for i in range(1, n + 1):
             prod = plans[i - 1]
@@ -161,6 +162,7 @@ class _DecoderStackFn(Function):
                   act=prod.lrelu, dump=dump, bias=bs[i - 1], aux=aux, s_out=s_i, stage_ws=st_c if cons is not None else None)
             bounds.append(s_i)
             if cons is not None:
+                packs[i] = _packed(cons, ws[i])
                 check(lib.hmvae_conv_tc_run(cons.handle, 0, ptr(packs[i][0]), b, geo.t_in[i], ptr(st_c), ptr(dump_c), stream()), "conv_tc_run")
                 dump = dump_c
         ctx.spec, ctx.b, ctx.concat = spec, b, concat
@@ -282,7 +284,8 @@ class _EncoderStackFn(Function):
         bounds = [x]
         st, dump = _bufs(plans[0], 0, b, geo.t_in[0])
         check(lib.hmvae_conv_tc_stage(plans[0].handle, 0, ptr(x), None, b, geo.t_in[0], ptr(st), stream()), "conv_tc_stage")
-        packs = [_packed(plans[i], ws[i]) for i in range(n)]
+        packs = [None] * n                                   # each conv waits for ITS packed weights only (packing runs on the side stream)
+        packs[0] = _packed(plans[0], ws[0])
         check(lib.hmvae_conv_tc_run(plans[0].handle, 0, ptr(packs[0][0]), b, geo.t_in[0], ptr(st), ptr(dump), stream()), "conv_tc_run")
         for i in range(1, n + 1):
             prod = plans[i - 1]
@@ -296,6 +299,7 @@ class _EncoderStackFn(Function):
                   pool=pool, dump=dump, bias=bs[i - 1], s_out=s_i, stage_ws=st_c if cons is not None else None)
             bounds.append(s_i)
             if cons is not None:
+                packs[i] = _packed(cons, ws[i])
                 check(lib.hmvae_conv_tc_run(cons.handle, 0, ptr(packs[i][0]), b, geo.t_in[i], ptr(st_c), ptr(dump_c), stream()), "conv_tc_run")
                 dump = dump_c
         ctx.spec, ctx.b = spec, b

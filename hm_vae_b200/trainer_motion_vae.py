@@ -270,7 +270,8 @@ class Trainer(nn.Module):
         ops._force_repack = True            # the packed tf32 weight copies must be refreshed inside every replay
         self._sync.enabled = not multi      # no NCCL inside the graph: with world > 1 only forward+backward is captured
         try:
-            with torch.cuda.graph(graph):
+            cap = torch.cuda.Stream(priority=ops.main_stream_priority())
+            with torch.cuda.graph(graph, stream=cap):
                 static_out = self._fwd_bwd(static_in, hp, iterations) if multi else self._device_step(static_in, hp, iterations)
         finally:
             ops._force_repack = False

@@ -211,6 +211,33 @@ int hmvae_latent_fwd(const float* dist, const float* eps, float* z, float* kl_ou
 int hmvae_latent_bwd(const float* dist, const float* eps, const float* dz, const float* dkl, float* ddist, long rows,
                      int d, float kl_scale, void* stream);
 
+/* The latent bottleneck of the hierarchy, up to 4 levels per launch (seq_two_hier_sa_vae.py:159-164 encoder heads `nn.Linear`,
+ * :357-391 / :419-428 reparametrise + kl_loss, :225-229 / :267 decoder heads `nn.Linear`), one row per (sequence, edge):
+ *   fwd: dist = x enc_w^T + enc_b;  z = eps*exp(lv/2)+mu ((mu|lv) = dist; eps NULL: z = mu);  kl_acc[0] += sum of KL row sums
+ *        (atomic; caller zeroes);  feat = z dec_w^T + dec_b.
+ *   bwd: gz = gfeat dec_w;  gdist = [gz + s*mu | gz*eps*exp(lv/2)/2 + s*(exp(lv)-1)/2] with s = kl_scale;  gx = gdist enc_w.
+ * Weight gradients are NOT produced here: use hmvae_linear_bwd on (x, gdist) and (z, gfeat).
+ * x / feat / gfeat / gx: [rows, features]; dist / gdist: [rows, 2d]; z / eps: [rows, d]; enc_w [2d, features]; dec_w [features, d]. */
+typedef struct {
+  int rows, features, d;
+  float kl_scale;
+  const float* x;
+  const float* enc_w;
+  const float* enc_b;
+  const float* eps;
+  const float* dec_w;
+  const float* dec_b;
+  float* dist;
+  float* z;
+  float* feat;
+  float* kl_acc;
+  const float* gfeat;
+  float* gdist;
+  float* gx;
+} hmvae_head_level;
+int hmvae_latent_heads_fwd(const hmvae_head_level* levels, int n_levels, void* stream);
+int hmvae_latent_heads_bwd(const hmvae_head_level* levels, int n_levels, void* stream);
+
 /* One kernel for: GT FK (no grad), rot6d->R, FK on the prediction, the three MSEs and d(total)/d(x6_pred).
  * x6_pred: decoder output, NCW [B, 24*6, T] (ncw=1) or [B, T, 24*6] (ncw=0); gt_6d [B,T,144]; gt_rotmat [B,T,216].
  * losses: device float[4], ATOMICALLY accumulated (caller zeroes): {sum sq 6d, sum sq rot, sum sq pos, unused}.

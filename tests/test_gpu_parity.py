@@ -695,10 +695,20 @@ def test_latent_optimisation_vs_reference_golden(impl, graph, tol, smpl):
             assert np.mean(np.abs(zk - zr) > 50 * tol) <= 0.02 and rel_l2(zk, zr) < 5e-2 or not np.any(zr)
     # decoded motion of the LAST iteration: on the TF32 path it is decoded from latents / decoder weights that went through six
     # Adam steps (see above: a handful of +-0.1 sign flips) => 10 x tol there; the fp32 path holds tol itself
-    otol = tol if impl == ops.IMPL_SIMT else 10 * tol
+    otol = tol if impl == ops.IMPL_SIMT else 5e-2
     assert rel_l2(res["out_6d"].cpu(), g["out_6d"]) < otol
     assert rel_l2(res["out_rot_mat"].cpu(), g["out_rot_mat"]) < otol
     assert rel_l2(res["out_pose_pos"].cpu(), g["out_pose_pos"]) < otol
+    if impl != ops.IMPL_SIMT:
+        # ... and the decoded motion of the FIRST iteration (no Adam step in between) holds tol against the oracle
+        ora = O.HMVAEOracle(hp, smpl["parents"].tolist(), torch.from_numpy(smpl["offsets"])).init(seed=0)
+        ref1 = ora.latent_optimise(z_init, t6, tR, mask, hp, prev_epochs=prev_epochs, opt_it=1)
+        model1, _ = _model_with_oracle_weights(hp, smpl)
+        res1 = model1.optimize_latent(t6.to(DEV), tR.to(DEV), mask.to(DEV), hp, z_vec_list=z_init, prev_epochs=prev_epochs, opt_it=1,
+                                      cuda_graph=False)
+        for key in ("out_6d", "out_rot_mat", "out_pose_pos"):
+            assert rel_l2(res1[key].cpu(), ref1[key]) < tol, key
+        np.testing.assert_allclose(res1["losses"].cpu().numpy()[:, [0, 1, 2, 5]], ref1["losses"].numpy()[:, [0, 1, 2, 5]], rtol=tol)
     # the decoder copy moved (and the model's own decoder did not)
     moved = dict(res["decoder"].named_parameters())
     for k, p in model.dec.named_parameters():
@@ -746,4 +756,50 @@ def test_stack_path_matches_per_layer_path(tag, hp, bs, iters, smpl):
         g1 = out[True]["grads"][k]
         assert (g0 is None) == (g1 is None), k
         if g0 is not None and float(g0.abs().max()) > 0:
-            assert rel_l2(g1, g0) < 2e-3, (k, rel_l2(g1, g0))
+            # different summation order of the split-K partials => last-bit differences before the TF32 rounding of the next layer's
+            # staging => the usual LeakyReLU-flip noise, growing towards the first encoder layer (measured 3.4e-3 there)
+            assert rel_l2(g1, g0) < 1e-2, (k, rel_l2(g1, g0))
+
+
+@pytest.mark.parametrize("detach", [False, True])
+def test_latent_heads_vs_torch(detach):
+    """hmvae_latent_heads_fwd / _bwd (encoder head + reparametrise + KL + decoder head, two levels in one launch) against the
+    same chain written with torch ops (seq_two_hier_sa_vae.py:159-164, 419-428, 267), values and every gradient, 1e-5."""
+    gen = torch.Generator().manual_seed(11)
+    B, specs = 5, [(14, 384, 12), (7, 384, 24)]          # (edges, features, latent width): the len64 shallow / deep levels
+    kl_w = [0.003, 0.003]
+    ref_t, my_t, metas = [], [], []
+    acc = torch.zeros(8, device=DEV)
+    for l, (k, f, d) in enumerate(specs):
+        ts = [torch.randn(B, k, f, generator=gen), torch.randn(2 * d, f, generator=gen) * 0.05, torch.randn(2 * d, generator=gen) * 0.1,
+              torch.randn(f, d, generator=gen) * 0.2, torch.randn(f, generator=gen) * 0.1]
+        eps = torch.randn(B * k, d, generator=gen)
+        ref_t.append([t.clone().requires_grad_(True) for t in ts] + [eps])
+        my_t.append([t.clone().to(DEV).requires_grad_(True) for t in ts] + [eps.to(DEV)])
+        metas.append(dict(d=d, kl_scale=kl_w[l] / (B * k), kl_acc=acc[4 + l:5 + l], detach=(detach and l == 0)))
+    gf = [torch.randn(B, k, f, generator=gen) for k, f, d in specs]
+    # torch reference
+    total, ref_feats, ref_kl = 0.0, [], []
+    for l, ((k, f, d), (x, ew, eb, dw, db, eps)) in enumerate(zip(specs, ref_t)):
+        dist = torch.nn.functional.linear(x, ew, eb)
+        if metas[l]["detach"]:
+            dist = dist.detach()
+        mu, lv = dist[..., :d].reshape(-1, d), dist[..., d:].reshape(-1, d)
+        z = eps * torch.exp(0.5 * lv) + mu
+        kl = O.kl_loss(lv, mu)
+        feat = torch.nn.functional.linear(z.view(B, k, d), dw, db)
+        ref_feats.append(feat)
+        ref_kl.append(float(kl))
+        total = total + (feat * gf[l]).sum() + kl_w[l] * kl
+    total.backward()
+    feats, dists = ops.latent_heads(metas, [t for lvl in my_t for t in lvl])
+    torch.autograd.backward(list(feats), [g.to(DEV) for g in gf])
+    torch.cuda.synchronize()
+    for l, (k, f, d) in enumerate(specs):
+        assert rel_l2(feats[l].detach().cpu(), ref_feats[l].detach()) < 1e-5
+        np.testing.assert_allclose(float(acc[4 + l]) / (B * k), ref_kl[l], rtol=1e-5)
+        for name, a, b in zip(("x", "enc_w", "enc_b", "dec_w", "dec_b"), my_t[l][:5], ref_t[l][:5]):
+            if b.grad is None or float(b.grad.abs().max()) == 0.0:
+                assert a.grad is None or float(a.grad.abs().max()) == 0.0, (l, name)
+            else:
+                assert rel_l2(a.grad.cpu(), b.grad) < 1e-5, (l, name, rel_l2(a.grad.cpu(), b.grad))
