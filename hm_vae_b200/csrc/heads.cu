@@ -15,9 +15,10 @@
 
 namespace hmvae {
 
-constexpr int HD_ROWS = 8;
+constexpr int HD_ROWS = 4;
 constexpr int HD_MAXL = 4;
-constexpr int HD_THREADS = 128;
+constexpr int HD_THREADS = 256;
+constexpr int HD_WCH = 12;           // weight elements per lane held in registers (covers 384 features per pass)
 constexpr int HD_MAXD = 32;          // latent width per edge
 
 struct HeadLevel {
@@ -75,10 +76,23 @@ __global__ void __launch_bounds__(HD_THREADS) heads_fwd_kernel(const __grid_cons
 #pragma unroll
     for (int r = 0; r < HD_ROWS; ++r) acc[r] = 0.f;
     const float* wrow = L.We + (size_t)o * F;
-    for (int i = lane; i < F; i += 32) {
-      const float w = wrow[i];
+    for (int i0 = 0; i0 < F; i0 += 32 * HD_WCH) {
+      // all loads of the pass are issued before the first use (a one-load-per-iteration loop is a chain of L2 latencies:
+      // the first version of this kernel took 41 us)
+      float w[HD_WCH];
 #pragma unroll
-      for (int r = 0; r < HD_ROWS; ++r) acc[r] = fmaf(w, xs[r * F + i], acc[r]);
+      for (int k = 0; k < HD_WCH; ++k) {
+        const int i = i0 + lane + 32 * k;
+        w[k] = i < F ? wrow[i] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < HD_WCH; ++k) {
+        const int i = i0 + lane + 32 * k;
+        if (i < F) {
+#pragma unroll
+          for (int r = 0; r < HD_ROWS; ++r) acc[r] = fmaf(w[k], xs[r * F + i], acc[r]);
+        }
+      }
     }
     const float b = L.be ? L.be[o] : 0.f;
 #pragma unroll
@@ -119,6 +133,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_fwd_kernel(const __grid_cons
 #pragma unroll
     for (int r = 0; r < HD_ROWS; ++r) acc[r] = b;
     const float* wrow = L.Wd + (size_t)j * d;
+#pragma unroll 8
     for (int c = 0; c < d; ++c) {
       const float w = wrow[c];
 #pragma unroll
@@ -153,10 +168,21 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const __grid_cons
     float acc[HD_ROWS];
 #pragma unroll
     for (int r = 0; r < HD_ROWS; ++r) acc[r] = 0.f;
-    for (int j = lane; j < F; j += 32) {
-      const float w = L.Wd[(size_t)j * d + c];
+    for (int j0 = 0; j0 < F; j0 += 32 * HD_WCH) {
+      float w[HD_WCH];
 #pragma unroll
-      for (int r = 0; r < HD_ROWS; ++r) acc[r] = fmaf(w, gs[r * F + j], acc[r]);
+      for (int k = 0; k < HD_WCH; ++k) {
+        const int j = j0 + lane + 32 * k;
+        w[k] = j < F ? L.Wd[(size_t)j * d + c] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < HD_WCH; ++k) {
+        const int j = j0 + lane + 32 * k;
+        if (j < F) {
+#pragma unroll
+          for (int r = 0; r < HD_ROWS; ++r) acc[r] = fmaf(w[k], gs[r * F + j], acc[r]);
+        }
+      }
     }
 #pragma unroll
     for (int r = 0; r < HD_ROWS; ++r) {
@@ -186,6 +212,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const __grid_cons
     float acc[HD_ROWS];
 #pragma unroll
     for (int r = 0; r < HD_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll 8
     for (int o = 0; o < d2; ++o) {
       const float w = L.We[(size_t)o * F + i];
 #pragma unroll

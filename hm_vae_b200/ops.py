@@ -82,10 +82,20 @@ def main_stream_priority():
     return int(os.environ.get("HMVAE_MAIN_PRIORITY", "-1"))
 
 
+def _eps_stream():
+    """Stream of the N(0,1) draws of a step: they depend on nothing, but queued behind the weight packing they would come too late,
+    and queued before it they delay the first conv (tools/timeline.py)."""
+    if _overlap.get("eps") is None:
+        _overlap["eps"] = torch.cuda.Stream(priority=0)
+    return _overlap["eps"]
+
+
 def _wgrad_stream():
-    """Weight gradients of consecutive layers go round-robin to HMVAE_WGRAD_STREAMS side streams (default 1: measured 1-4
-    streams within run-to-run noise, 0.875-0.914 ms per step -- the dgrad chain on the main stream is the critical path)."""
-    n = max(1, int(os.environ.get("HMVAE_WGRAD_STREAMS", "1")))
+    """Weight gradients of consecutive layers go round-robin to HMVAE_WGRAD_STREAMS side streams.  Default 2: with the linked
+    stack path the data-gradient chain is short enough that ONE stream of weight gradients (prep -> bias -> tcgen05 kernel per
+    layer, ~375 us of sequential kernels) became the longer chain of the backward pass (same box, graph replay: 836 / 807 / 826 us
+    per step with 1 / 2 / 3 streams)."""
+    n = max(1, int(os.environ.get("HMVAE_WGRAD_STREAMS", "2")))
     pool = _overlap.setdefault("pool", [])
     while len(pool) < n:
         pool.append(_side_stream() if not pool else torch.cuda.Stream(priority=0))
@@ -600,6 +610,7 @@ class _HeadsFn(Function):
     @staticmethod
     def forward(ctx, levels, *tensors):
         n = len(levels)
+        ctx.set_materialize_grads(False)
         arr = (_lib.HeadLevel * n)()
         xs, feats, dists, zs, keep = [], [], [], [], []
         for l, meta in enumerate(levels):

@@ -295,7 +295,7 @@ class TwoHierSAVAEModel(nn.Module):
                 eps = self._draw_eps(None, dev, eps_list)
             else:
                 # the four N(0,1) draws depend on nothing: issue them on the side stream, off the encoder's critical path
-                side, main = ops._side_stream(), torch.cuda.current_stream()
+                side, main = ops._eps_stream(), torch.cuda.current_stream()
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     eps = self._draw_eps([(bs * k_edges[i], lat[i]) for i in range(n)], dev, None)

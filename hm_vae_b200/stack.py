@@ -138,6 +138,7 @@ class _DecoderStackFn(Function):
     def forward(ctx, spec, feat0, feat_last, *params):
         plans, geo, b = spec["plans"], spec["geo"], feat0.shape[0]
         n = len(plans)
+        ctx.set_materialize_grads(False)
         ws, bs = params[:n], params[n:]                      # weights, biases (None where the conv has none)
         feat0 = feat0.contiguous()
         concat = feat_last is not None
@@ -176,6 +177,8 @@ class _DecoderStackFn(Function):
         spec, b = ctx.spec, ctx.b
         plans, geo = spec["plans"], spec["geo"]
         n = len(plans)
+        if gout is None:
+            return (None,) * (3 + 2 * n)
         saved = ctx.saved_tensors
         bounds, ws = saved[:n + 1], saved[n + 1:2 * n + 1]
         bias_iter = iter(saved[2 * n + 1:])
@@ -278,6 +281,7 @@ class _EncoderStackFn(Function):
     def forward(ctx, spec, x, *params):
         plans, geo, pools, b = spec["plans"], spec["geo"], spec["pools"], x.shape[0]
         n = len(plans)
+        ctx.set_materialize_grads(False)      # levels without a latent head get None, not a zero tensor (3 fill kernels + 3 dead adds)
         ws, bs = params[:n], params[n:]
         x = x.contiguous()
         dev = x.device
