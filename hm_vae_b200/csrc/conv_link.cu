@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128, 3) conv_link_kernel(const __grid_constant
       }
     }
     // ---- the boundary tensor itself (NCW): 4 channel rows x (i1 - i0) consecutive steps, written by lane 0 of the item
-    if (zl == 0) {
+    if (zl == 0 && L.S != nullptr) {
       float* sp = L.S + (((size_t)b * L.ES + e) * L.cs + c0) * L.TS + i0;
       const int len = i1 - i0;
       const float rowv[4][LK_CH] = {{sv[1].x, sv[2].x}, {sv[1].y, sv[2].y}, {sv[1].z, sv[2].z}, {sv[1].w, sv[2].w}};
@@ -343,7 +343,7 @@ using namespace hmvae;
 static const char* link_build(const hmvae_conv_link_desc& d, LinkArgs* out) {
   LinkArgs& L = *out;
   memset(&L, 0, sizeof(L));
-  if (!d.prod || !d.dump || !d.s_out) return "null pointer";
+  if (!d.prod || !d.dump || (!d.s_out && !d.cons)) return "null pointer";      // s_out may be NULL (inference: staging only)
   if (d.kind < 0 || d.kind > 2 || d.batch < 1) return "bad kind / batch";
   const int pmode = d.kind == 0 ? 0 : 1;
   if (!tc_geometry(d.prod, d.batch, d.prod_t, pmode, &L.P)) return "producer geometry not supported by the tcgen05 path";
@@ -456,7 +456,7 @@ extern "C" int hmvae_conv_link_supported(const hmvae_conv_link_desc* desc) {
   hmvae_conv_link_desc d = *desc;
   static float dummy;
   if (!d.dump) d.dump = &dummy;
-  if (!d.s_out) d.s_out = &dummy;
+  if (!d.s_out && !d.cons) d.s_out = &dummy;
   if (d.cons && !d.stage_ws) d.stage_ws = &dummy;
   LinkArgs L;
   return link_build(d, &L) == nullptr ? 1 : 0;
@@ -470,7 +470,7 @@ extern "C" int hmvae_conv_link(const hmvae_conv_link_desc* desc, void* stream) {
     snprintf(g_err, sizeof(g_err), "hmvae: conv_link: %s", err);
     return HMVAE_E_ARG;
   }
-  if (!aligned16(desc->dump) || !aligned16(desc->s_out) || (desc->cons && !aligned16(desc->stage_ws)))
+  if (!aligned16(desc->dump) || (desc->s_out && !aligned16(desc->s_out)) || (desc->cons && !aligned16(desc->stage_ws)))
     return fail_arg("conv_link: buffers must be 16-byte aligned");
   const long items = (long)L.P.B * L.ES * ((L.cs + 3) / 4) * ((L.TS + LK_CH - 1) / LK_CH);
   // lanes per item: enough to cut the split-K walk to <= 2-3 partials per lane, but only while the grid stays small

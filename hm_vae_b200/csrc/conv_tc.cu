@@ -457,6 +457,50 @@ static void tc_build_layer(const hmvae_conv_plan* plan, int mode, TcLayer* L) {
       if (mode == 0) lists[j].push_back(plan->nb_idx[m]);
       else lists[plan->nb_idx[m]].push_back(j);
     }
+  // ---- dense joint groups for narrow layers.  A kind::tf32 MMA costs the same ~63 cycles for every N <= 128, and with few
+  // channels per joint (6 or 12) the sparse formulation issues one N = 16..64 MMA per RUN of consecutive output joints that share
+  // an input joint -- the last decoder level is then bound by the MMA COUNT (4050 per 128-row tile; tools/tc_phases.py: 21 of its
+  // 32 us are issue time).  Here a group is GJ output joints packed at 8-channel granularity (N = GJ * n_pad ~ 96 columns), every
+  // input joint in the union of the group's neighbour lists feeds ONE MMA over the whole group, and the weights of the (joint,
+  // input joint) pairs that are masked are zeros in the packed copy (never written: the buffer is zero-initialised).  Chosen per
+  // (layer, mode) when it cuts the MMA count by >= 1.4x (HMVAE_TC_DENSE: -1 auto, 0 never, 1 whenever the layer is narrow).
+  bool dense = false;
+  {
+    const int want = env_int("HMVAE_TC_DENSE", -1);
+    const int np8 = rup(L->n_real, 8);
+    const int cols = env_int("HMVAE_TC_DENSE_COLS", 96);
+    int gj = cols / np8;
+    gj &= ~1;                                        // N = gj * np8 must be a multiple of 16
+    if (want != 0 && np8 <= 16 && gj >= 2 && a.J > L->GJ) {
+      long sparse_units = 0, dense_units = 0;
+      for (int g = 0; g * L->GJ < a.J; ++g)
+        for (int n = 0; n < a.J; ++n) {
+          int prev = -2, runs = 0;
+          for (int jl = 0; jl < L->GJ && g * L->GJ + jl < a.J; ++jl)
+            for (int kn : lists[g * L->GJ + jl])
+              if (kn == n) { runs += (jl != prev + 1); prev = jl; }
+          sparse_units += runs;
+        }
+      for (int g = 0; g * gj < a.J; ++g)
+        for (int n = 0; n < a.J; ++n) {
+          bool any = false;
+          for (int jl = 0; jl < gj && g * gj + jl < a.J; ++jl)
+            for (int kn : lists[g * gj + jl]) any |= kn == n;
+          dense_units += any;
+        }
+      dense = want == 1 || dense_units * 14 <= sparse_units * 10;
+      if (dense) {
+        L->n_pad = np8;
+        L->GJ = gj;
+        L->groups = (a.J + gj - 1) / gj;
+        // one stage = all GJ slots: keep it around 48 KB
+        L->KC = 8;
+        const int kcs[3] = {32, 24, 16};
+        for (int i = 2; i >= 0; --i)
+          if (L->ck_pad % kcs[i] == 0 && (long)gj * a.K * (kcs[i] / 4) * np8 * 16 <= 48 * 1024) L->KC = kcs[i];
+      }
+    }
+  }
   const int ncb = L->ck_pad / L->KC, qpb = L->KC / 4;
   L->slots.assign((size_t)L->groups * a.J, {});
   L->base.assign((size_t)L->groups * a.J, 0);
@@ -473,6 +517,10 @@ static void tc_build_layer(const hmvae_conv_plan* plan, int mode, TcLayer* L) {
       for (int jl = 0; jl < L->GJ && g * L->GJ + jl < a.J; ++jl)
         for (int kn : lists[g * L->GJ + jl])
           if (kn == n) sl.push_back(jl);
+      if (dense && !sl.empty()) {                      // every joint of the group is a slot (absent pairs: zero weights)
+        sl.clear();
+        for (int jl = 0; jl < L->GJ; ++jl) sl.push_back(jl);
+      }
       const int cnt = (int)sl.size();
       w.cnt[n] = cnt;
       w.base[n] = (int)off;

@@ -107,7 +107,7 @@ class Encoder(nn.Module):
 
         ``needed``: optional set of level indices whose latent heads are required (others return None)."""
         z_vector_list = []
-        levels = stack.encoder_forward(self, input)          # all level outputs through the linked stack, or None
+        levels = stack.encoder_forward(self, input, needed)  # all level outputs through the linked stack, or None
         for i in range(len(self.layers)):
             input = levels[i] if levels is not None else self._level(i, input)
             if needed is not None and i not in needed:
@@ -376,7 +376,7 @@ class TwoHierSAVAEModel(nn.Module):
         enc, dec = self.enc, self.dec
         if len(dec.layers) != n or hp['extra_conv']:
             return None
-        outs = stack.encoder_forward(enc, x)
+        outs = stack.encoder_forward(enc, x, {0, n - 1})
         if outs is None:
             return None
         bs = x.shape[0]

@@ -145,6 +145,7 @@ class _DecoderStackFn(Function):
         if concat:
             feat_last = feat_last.contiguous()
         dev = feat0.device
+        spec_grad = any(ctx.needs_input_grad)
         bounds = [feat0]                                     # bounds[i] = source tensor of conv i
         st, dump = _bufs(plans[0], 0, b, geo.t_in[0])
         check(lib.hmvae_conv_tc_stage(plans[0].handle, 0, ptr(feat0), None, b, geo.t_in[0], ptr(st), stream()), "conv_tc_stage")
@@ -155,7 +156,9 @@ class _DecoderStackFn(Function):
             prod = plans[i - 1]
             cons = plans[i] if i < n else None
             chans = prod.joints * prod.out_joint_stride
-            s_i = torch.empty((b, chans, geo.t_out[i - 1]), device=dev, dtype=torch.float32)
+            # interior boundary tensors are only needed again by the backward pass: not written under no_grad
+            keep = cons is None or spec_grad
+            s_i = torch.empty((b, chans, geo.t_out[i - 1]), device=dev, dtype=torch.float32) if keep else None
             aux = feat_last if (concat and i == n - 1) else None
             if cons is not None:
                 st_c, dump_c = _bufs(cons, 0, b, geo.t_in[i])
@@ -166,10 +169,11 @@ class _DecoderStackFn(Function):
                 packs[i] = _packed(cons, ws[i])
                 check(lib.hmvae_conv_tc_run(cons.handle, 0, ptr(packs[i][0]), b, geo.t_in[i], ptr(st_c), ptr(dump_c), stream()), "conv_tc_run")
                 dump = dump_c
-        ctx.spec, ctx.b, ctx.concat = spec, b, concat
-        ctx.packs_d = [p[1] for p in packs]
-        ctx.has_bias = [x is not None for x in bs]
-        ctx.save_for_backward(*bounds, *ws, *[x for x in bs if x is not None])
+        if spec_grad:
+            ctx.spec, ctx.b, ctx.concat = spec, b, concat
+            ctx.packs_d = [p[1] for p in packs]
+            ctx.has_bias = [x is not None for x in bs]
+            ctx.save_for_backward(*bounds, *ws, *[x for x in bs if x is not None])
         return bounds[n]
 
     @staticmethod
@@ -285,6 +289,7 @@ class _EncoderStackFn(Function):
         ws, bs = params[:n], params[n:]
         x = x.contiguous()
         dev = x.device
+        spec_grad = any(ctx.needs_input_grad)
         bounds = [x]
         st, dump = _bufs(plans[0], 0, b, geo.t_in[0])
         check(lib.hmvae_conv_tc_stage(plans[0].handle, 0, ptr(x), None, b, geo.t_in[0], ptr(st), stream()), "conv_tc_stage")
@@ -296,7 +301,8 @@ class _EncoderStackFn(Function):
             cons = plans[i] if i < n else None
             pool = pools[i - 1]
             e_out = len(pool) if pool is not None else prod.joints
-            s_i = torch.empty((b, e_out * prod.co, geo.t_out[i - 1]), device=dev, dtype=torch.float32)
+            keep = cons is None or spec_grad or (i - 1) in spec["needed"]
+            s_i = torch.empty((b, e_out * prod.co, geo.t_out[i - 1]), device=dev, dtype=torch.float32) if keep else None
             if cons is not None:
                 st_c, dump_c = _bufs(cons, 0, b, geo.t_in[i])
             _link(kind=0, b=b, prod=prod, prod_t=geo.t_in[i - 1], cons=cons, cons_t=geo.t_in[i] if cons is not None else 0, act=True,
@@ -306,11 +312,12 @@ class _EncoderStackFn(Function):
                 packs[i] = _packed(cons, ws[i])
                 check(lib.hmvae_conv_tc_run(cons.handle, 0, ptr(packs[i][0]), b, geo.t_in[i], ptr(st_c), ptr(dump_c), stream()), "conv_tc_run")
                 dump = dump_c
-        ctx.spec, ctx.b = spec, b
-        ctx.packs_d = [p[1] for p in packs]
-        ctx.has_bias = [v is not None for v in bs]
-        ctx.save_for_backward(*bounds, *ws, *[v for v in bs if v is not None])
-        return tuple(bounds[1:])
+        if spec_grad:
+            ctx.spec, ctx.b = spec, b
+            ctx.packs_d = [p[1] for p in packs]
+            ctx.has_bias = [v is not None for v in bs]
+            ctx.save_for_backward(*bounds, *ws, *[v for v in bs if v is not None])
+        return tuple(t if t is not None else x.new_empty(0) for t in bounds[1:])
 
     @staticmethod
     def backward(ctx, *gs):
@@ -398,13 +405,15 @@ def encoder_spec(enc, b, t0):
     return spec
 
 
-def encoder_forward(enc, x):
-    """All level outputs of Encoder.forward's conv stack ([pooled, activated] per level), or None (caller falls back)."""
+def encoder_forward(enc, x, needed=None):
+    """All level outputs of Encoder.forward's conv stack ([pooled, activated] per level), or None (caller falls back).
+    ``needed``: levels whose output the caller reads (None = all); under no_grad the others are not written (empty tensors)."""
     if not _enabled or ops._conv_impl == ops.IMPL_SIMT or x.requires_grad:
         return None
     spec = encoder_spec(enc, x.shape[0], x.shape[2])
     if spec is None:
         return None
+    spec = dict(spec, needed=set(range(len(enc.convs))) if needed is None else set(needed))
     ws = [c.weight for c in enc.convs]
     bs = [c.bias for c in enc.convs]
     return _EncoderStackFn.apply(spec, x, *ws, *bs)

@@ -124,6 +124,7 @@ int hmvae_conv_tc_finish(const hmvae_conv_plan* plan, int mode, const void* dump
  *                       activated output in the layout of S when it fuses LeakyReLU.
  *   kind 2 (backward, encoder side): producer = dgrad of conv P whose input is pool(+LeakyReLU) of conv C's output;
  *                       S = gradient of C's raw output = pool^T(lrelu'(sact) * (dgrad_P + add)); sact / add: [batch, J_P*ci_P, T_P].
+ * s_out may be NULL when a consumer is given (inference: nothing needs the boundary tensor again).
  * stage_ws: the consumer's staging buffer -- PERSISTENT and ZERO-INITIALISED by the caller (hmvae_conv_tc_sizes bytes): the kernel
  * writes only real values, padding rows / channels and zero-inserted positions must stay 0.
  * hmvae_conv_link_supported: 1 if the descriptor's geometry can take this path (buffers may be NULL). */

@@ -8,7 +8,8 @@ gradients: G = ((g_0 + g_1) + ...) * (1/W) in fp32, then torch.optim.Adam.  With
 (an update is +-lr whatever the magnitude of a rounding-level gradient), so the bounds are tight:
     reduced gradient before Adam (recovered from exp_avg after step 1: m_1 = (1-b1) * (G + wd*p))   <= 1e-6 relative-L2
     exp_avg / exp_avg_sq after 3 steps                                                              <= 1e-5 relative-L2
-    parameters after 3 steps                                             <= 5e-7 absolute (2 ulp of the largest |p| ~ 4; one update = 1e-4)
+    parameters after 3 steps                                             <= 5e-7 absolute (2 ulp of the largest |p| ~ 4; one update = 1e-4);
+                                                                            1e-5 on the NVSwitch multicast path (see PARAM_TOL)
     all ranks hold bit-identical parameters.
 Exit code 0 = pass.  tests/test_dp_multi_gpu.py spawns this when >= 2 GPUs are visible."""
 import os
@@ -25,6 +26,12 @@ rank, world, local = ddp.init_from_env("nccl")
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 LR, WD, B1, B2 = 1e-4, 1e-4, 0.9, 0.999
+# Parameter bound.  Unicast peer loads add the ranks' gradients in the fixed order 0..W-1, exactly like the reference sum: 5e-7
+# (2 ulp of |p| ~ 4).  The NVSwitch multicast path (multimem.ld_reduce) adds them INSIDE the switch in a hardware-defined order:
+# the reduced gradient still agrees to 1e-6 relative-L2, but the handful of elements whose first gradients are ~1e-6 (3.4 M
+# elements of N(0, 1/W)) see a different m/sqrt(v) ratio -- measured 2.95e-6 on one element at W = 4 -- so 1e-5 there (10 % of
+# ONE lr step); the reduced gradient and the moments keep their tight bounds on both paths.
+PARAM_TOL = 1e-5 if os.environ.get("HMVAE_DP_MULTICAST", "0") == "1" else 5e-7
 shapes = [(288, 144, 15), (288,), (24, 384), (3,), (7,), (672, 336, 15), (336,)]
 DEAD = 2                                   # never receives a gradient: must stay untouched (torch skips grad=None)
 
@@ -87,7 +94,7 @@ for i, (a, b) in enumerate(zip(mine, ref_p)):
     em, ev = rel_l2(sd["state"][i]["exp_avg"], ref.state[b]["exp_avg"]), rel_l2(sd["state"][i]["exp_avg_sq"], ref.state[b]["exp_avg_sq"])
     if em > 1e-5 or ev > 1e-5:
         fails.append("tensor %d: exp_avg rel-L2 %.3e, exp_avg_sq rel-L2 %.3e" % (i, em, ev))
-    if d > 5e-7:
+    if d > PARAM_TOL:
         fails.append("tensor %d: parameter max abs diff %.3e" % (i, d))
 if DEAD in sd["state"]:
     fails.append("dead parameter has optimiser state")
