@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(TcArgs p, const float
   pdl_wait();
   const ConvArgs& a = p.a;
   const int Tq = p.T + 2 * a.p;
-  const int tfill = (p.mode == 0) ? Tq : ((p.ntt > 1 ? 128 : Tq) + a.K - 1);
+  const int tfill = (p.mode == 0) ? (p.ntt > 1 ? 128 + a.K - 1 : Tq) : ((p.ntt > 1 ? 128 : Tq) + a.K - 1);
   const int nq = p.ck_pad / 4;             // 16-byte chunks per K-side joint
   const int qpb = p.KC / 4;                // chunks per stage block
   const long per_mt = (long)a.J * nq * p.Bt * tfill;
@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(TcArgs p, const float
     int row;
     if (p.mode == 0) {
       row = (a.s == 1) ? r * p.Bt + b : ((r & 1) * p.Tp2 + (r >> 1)) * p.Bt + b;
-      if (bb < p.B) {
+      const int qpos = (p.ntt > 1) ? r + (mt % p.ntt) * p.U : r;       // padded input position (time-tiled: window of tile tt)
+      if (bb < p.B && qpos < Tq) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (c0 + i < a.ci) v[i] = load_padded(src, a, bb, n, c0 + i, r, p.T);
+          if (c0 + i < a.ci) v[i] = load_padded(src, a, bb, n, c0 + i, qpos, p.T);
       }
     } else {
       row = r * p.Bt + b;
@@ -637,9 +638,15 @@ static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mod
   p.ntt = 1;
   p.U = (mode == 0) ? p.T_out : T;
   if (p.Tt < 1) return false;
-  if (p.Tt > 128) {
+  if (p.Tt > 128 && mode == 0) {
+    // fprop with more than 128 output steps per sequence (stride 1): tile tt of a sequence owns the output steps
+    // [tt*128, tt*128 + 128) and stages the 128 + K - 1 padded input rows they read (consecutive tiles overlap by K - 1 rows)
+    if (a.s != 1) return false;
+    p.ntt = (p.T_out + 127) / 128;
+    p.U = 128;
+    p.Bt = 1;
+  } else if (p.Tt > 128) {
     // dgrad of long sequences (trajectory model: T = 128, K = 31 => 158 padded rows): tile over time, one sequence per tile
-    if (mode == 0) return false;
     int n = 2;
     for (; n <= 64; ++n) {
       const int U = (T + n - 1) / n;
@@ -660,7 +667,7 @@ static bool tc_geometry_build(const hmvae_conv_plan* plan, int B, int T, int mod
       const int need = (p.Tp2 + (a.K - 1) / 2) * p.Bt + 128;
       p.rows_alloc = 2 * p.Tp2 * p.Bt > need ? 2 * p.Tp2 * p.Bt : need;
     }
-    const int fill = (a.s == 1) ? Tq * p.Bt : 2 * p.Tp2 * p.Bt;
+    const int fill = (p.ntt > 1) ? 128 + a.K - 1 : ((a.s == 1) ? Tq * p.Bt : 2 * p.Tp2 * p.Bt);
     if (fill > p.rows_alloc) p.rows_alloc = fill;
   } else {
     p.rows_alloc = (a.K - 1) * p.Bt + 128;

@@ -69,8 +69,16 @@ __device__ __forceinline__ float tc_dump_sum(const TcArgs& p, const float* __res
 // fprop result before the activation: conv sum + bias of conv-output joint j, channel o, sequence b, step t
 __device__ __forceinline__ float tc_fprop_value(const TcArgs& p, const float* __restrict__ dump, const float* __restrict__ bias,
                                                 int b, int j, int o, int t) {
-  const int mt = b / p.Bt;
-  float v = tc_dump_sum(p, dump, mt, j / p.GJ, t * p.Bt + (b - mt * p.Bt), (j % p.GJ) * p.n_pad + o);
+  int mt, row;
+  if (p.ntt > 1) {                       // time-tiled fprop: tile tt of sequence b holds the output steps [tt*U, tt*U + 128)
+    const int tt = t / p.U;
+    mt = b * p.ntt + tt;
+    row = t - tt * p.U;
+  } else {
+    mt = b / p.Bt;
+    row = t * p.Bt + (b - mt * p.Bt);
+  }
+  float v = tc_dump_sum(p, dump, mt, j / p.GJ, row, (j % p.GJ) * p.n_pad + o);
   if (bias) v += bias[j * p.a.co + o];
   return v;
 }

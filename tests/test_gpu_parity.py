@@ -259,6 +259,13 @@ def test_conv_layer_shapes_benchmarked_batch(golden_topology, shape):
     _conv_layer_case(golden_topology, shape, "auto", b)
 
 
+@pytest.mark.parametrize("shape", [(0, 3, 6, 31, 1, 256, False, None), (1, 6, 12, 15, 1, 200, False, None), (2, 12, 24, 15, 1, 130, False, None)])
+def test_conv_long_sequences_time_tiled(golden_topology, shape):
+    """More than 128 output steps per sequence: fprop AND dgrad are tiled over time on the tensor cores (no CUDA-core fallback:
+    _conv_layer_case asserts that), all three passes at 2e-3."""
+    _conv_layer_case(golden_topology, shape, "auto", 3)
+
+
 @pytest.mark.parametrize("shape", LAYER_SHAPES[:8])
 def test_conv_layer_shapes_b512(golden_topology, shape):
     """BASELINE config 4 batch (B=512): 256+ M tiles per layer, all three passes at 2e-3."""
