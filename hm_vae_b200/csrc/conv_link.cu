@@ -67,38 +67,43 @@ __device__ __forceinline__ size_t lk_stage_index(const TcArgs& C, int mt, int n,
   return ((((size_t)mt * C.a.J + n) * (nq / qpb) + cb) * qpb + h) * C.rows_alloc + row;
 }
 
-constexpr int LK_MAXK = 2 * LK_CH + 2;      // dump rows one thread accumulates side by side (kind 1 with upsample: 2*CH + 2)
+// dump rows one item accumulates side by side: forward CH + 2 (one-step halo for the consumer's upsample), decoder backward
+// 2*CH + 2 (upsample adjoint), encoder backward CH.  The kernel is instantiated per kind so that each variant only carries its own
+// accumulators (one generic kernel needed 154 registers: 12 warps per SM, and at B=512 ran at 1.3 TB/s).
+template <int KIND> struct LkRows { static constexpr int N = KIND == 0 ? LK_CH + 2 : (KIND == 1 ? 2 * LK_CH + 2 : LK_CH); };
 
 // acc[k] += sum over THIS LANE'S splits z = zl, zl + ZG, ... of dump[z][mt][g][row[k]][col4], for the k with row[k] >= 0.
 // The LK_MAXK loads of one split are independent and issued back to back, and the splits of one item are spread over ZG lanes
 // (an item at B=32 has up to 21 split-K partials x 2 pool members x 3 reflect folds: walked by one thread that is a ~10 us
 // dependent-latency chain; measured 20-30 us per link before this).
+template <int NK>
 __device__ __forceinline__ void lk_accum(const TcArgs& P, const float4* __restrict__ dump, int mt, int g, int col4, int zl, int ZG,
-                                         const int (&row)[LK_MAXK], float4 (&acc)[LK_MAXK]) {
+                                         const int (&row)[NK], float4 (&acc)[NK]) {
   const int dc4 = P.dcols >> 2;
   const size_t zstride = (size_t)P.mtiles * P.groups * 128 * dc4;
   const float4* d = dump + ((size_t)mt * P.groups + g) * 128 * dc4 + col4;
 #pragma unroll 2
   for (int z = zl; z < P.splits; z += ZG) {
-    float4 t[LK_MAXK];
+    float4 t[NK];
 #pragma unroll
-    for (int k = 0; k < LK_MAXK; ++k)
+    for (int k = 0; k < NK; ++k)
       t[k] = row[k] >= 0 ? d[(size_t)z * zstride + (size_t)row[k] * dc4] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < LK_MAXK; ++k) acc[k] = f4_add(acc[k], t[k]);
+    for (int k = 0; k < NK; ++k) acc[k] = f4_add(acc[k], t[k]);
   }
 }
 
 // gradient w.r.t. the producer conv's (virtual) input, joint n, channel group q, steps u0 .. u0 + nk - 1 (reflect-padding adjoint
 // folded in): G[k] += (this lane's share of the splits)
+template <int NK>
 __device__ __forceinline__ void lk_dgrad_rows(const TcArgs& P, const float4* __restrict__ dump, int b, int n, int q, int u0, int nk,
-                                              int zl, int ZG, float4 (&G)[LK_MAXK]) {
+                                              int zl, int ZG, float4 (&G)[NK]) {
   const ConvArgs& a = P.a;
   const int mt = b / P.Bt, bl = b - mt * P.Bt;
   const int g = n / P.GJ, col4 = ((n % P.GJ) * P.n_pad >> 2) + q;
-  int row[LK_MAXK];
+  int row[NK];
 #pragma unroll
-  for (int k = 0; k < LK_MAXK; ++k) {
+  for (int k = 0; k < NK; ++k) {
     const int u = u0 + k;
     row[k] = (k < nk && u >= 0 && u < P.T) ? (u + a.p) * P.Bt + bl : -1;
   }
@@ -106,7 +111,7 @@ __device__ __forceinline__ void lk_dgrad_rows(const TcArgs& P, const float4* __r
   if (a.pad_mode == 1) {
     bool any = false;
 #pragma unroll
-    for (int k = 0; k < LK_MAXK; ++k) {
+    for (int k = 0; k < NK; ++k) {
       const int u = u0 + k;
       row[k] = (k < nk && u >= 1 && u <= a.p && u < P.T) ? (a.p - u) * P.Bt + bl : -1;
       any |= row[k] >= 0;
@@ -114,7 +119,7 @@ __device__ __forceinline__ void lk_dgrad_rows(const TcArgs& P, const float4* __r
     if (any) lk_accum(P, dump, mt, g, col4, zl, ZG, row, G);
     any = false;
 #pragma unroll
-    for (int k = 0; k < LK_MAXK; ++k) {
+    for (int k = 0; k < NK; ++k) {
       const int u = u0 + k;
       row[k] = (k < nk && u >= 0 && u <= P.T - 2 && u >= P.T - 1 - a.p) ? (a.p + 2 * (P.T - 1) - u) * P.Bt + bl : -1;
       any |= row[k] >= 0;
@@ -124,10 +129,11 @@ __device__ __forceinline__ void lk_dgrad_rows(const TcArgs& P, const float4* __r
 }
 
 // butterfly sum over the ZG lanes of an item (fixed order: deterministic); every lane ends up with the total
-__device__ __forceinline__ void lk_reduce(float4 (&acc)[LK_MAXK], int ZG, unsigned mask) {
+template <int NK>
+__device__ __forceinline__ void lk_reduce(float4 (&acc)[NK], int ZG, unsigned mask) {
   for (int o = ZG >> 1; o > 0; o >>= 1) {
 #pragma unroll
-    for (int k = 0; k < LK_MAXK; ++k) {
+    for (int k = 0; k < NK; ++k) {
       acc[k].x += __shfl_xor_sync(mask, acc[k].x, o);
       acc[k].y += __shfl_xor_sync(mask, acc[k].y, o);
       acc[k].z += __shfl_xor_sync(mask, acc[k].z, o);
@@ -136,7 +142,9 @@ __device__ __forceinline__ void lk_reduce(float4 (&acc)[LK_MAXK], int ZG, unsign
   }
 }
 
-__global__ void __launch_bounds__(128, 3) conv_link_kernel(const __grid_constant__ LinkArgs L) {
+template <int KIND>
+__global__ void __launch_bounds__(128, 4) conv_link_kernel(const __grid_constant__ LinkArgs L) {
+  constexpr int NK = LkRows<KIND>::N;
   pdl_trigger();
   pdl_wait();
   const TcArgs& P = L.P;
@@ -159,21 +167,21 @@ __global__ void __launch_bounds__(128, 3) conv_link_kernel(const __grid_constant
     const int i0 = ch * LK_CH;
     const int i1 = (i0 + LK_CH < L.TS) ? i0 + LK_CH : L.TS;
     const int c0 = q << 2;
-    const bool up_f = L.kind == 0 && L.has_c && C.a.upsample;      // forward consumer blends neighbouring S steps: one-step halo
+    const bool up_f = KIND == 0 && L.has_c && C.a.upsample;      // forward consumer blends neighbouring S steps: one-step halo
     float4 sv[LK_CH + 2];                                            // sv[k] = S at step i0 - 1 + k
 #pragma unroll
     for (int k = 0; k < LK_CH + 2; ++k) sv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int klo = (up_f && i0 > 0) ? 0 : 1, khi = (up_f && i1 < L.TS) ? (i1 - i0 + 2) : (i1 - i0 + 1);
     const float scale = L.m_scale[e];
-    float4 acc[LK_MAXK];
+    float4 acc[NK];
 #pragma unroll
-    for (int k = 0; k < LK_MAXK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (L.kind == 0) {
+    for (int k = 0; k < NK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (KIND == 0) {
       if (c0 < L.cp) {
         const int mt = b / P.Bt, bl = b - mt * P.Bt;
-        int row[LK_MAXK];
+        int row[NK];
 #pragma unroll
-        for (int k = 0; k < LK_MAXK; ++k) row[k] = (k >= klo && k < khi) ? (i0 - 1 + k) * P.Bt + bl : -1;
+        for (int k = 0; k < NK; ++k) row[k] = (k >= klo && k < khi) ? (i0 - 1 + k) * P.Bt + bl : -1;
         float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int m = L.m_off[e]; m < L.m_off[e + 1]; ++m) {
           const int j = L.m_idx[m];
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(128, 3) conv_link_kernel(const __grid_constant
           sv[k] = v;
         }
       }
-    } else if (L.kind == 1) {
+    } else if constexpr (KIND == 1) {
       const bool up = P.a.upsample != 0;
       const int u0 = up ? 2 * i0 - 1 : i0;                           // acc[k] = gradient at conv-input step u0 + k
       const int nk = up ? 2 * (i1 - i0) + 2 : (i1 - i0);
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__(128, 3) conv_link_kernel(const __grid_constant
     // ---- scatter into the consumer's staged tiles; the (fan-out joint, step) pairs of an item are dealt round-robin to its lanes
     const int mtc = b / C.Bt, blc = b - mtc * C.Bt;
     int turn = 0;
-    if (L.kind == 0) {
+    if constexpr (KIND == 0) {
       const ConvArgs& ca = C.a;
       const int Tc = C.T;
       auto put = [&](int n, int u, float4 val) {
@@ -483,6 +491,9 @@ extern "C" int hmvae_conv_link(const hmvae_conv_link_desc* desc, void* stream) {
   const long total = items * zg;
   long blocks = (total + 127) / 128, cap = (long)num_sms() * 16;
   if (blocks < 1) blocks = 1;
-  launch_pdl(conv_link_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(128), 0, (cudaStream_t)stream, L);
+  const dim3 grid((unsigned)(blocks < cap ? blocks : cap));
+  if (L.kind == 0) launch_pdl(conv_link_kernel<0>, grid, dim3(128), 0, (cudaStream_t)stream, L);
+  else if (L.kind == 1) launch_pdl(conv_link_kernel<1>, grid, dim3(128), 0, (cudaStream_t)stream, L);
+  else launch_pdl(conv_link_kernel<2>, grid, dim3(128), 0, (cudaStream_t)stream, L);
   return check_launch("conv_link");
 }
