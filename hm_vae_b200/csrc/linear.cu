@@ -6,32 +6,66 @@
 namespace hmvae {
 
 // ---- y[r, o] = sum_i x[r, i] * w[o, i] + bias[o]      (both operands contiguous along the reduction)
-// One warp per (row, 8 outputs): lanes stride over i (128-byte coalesced loads), 8 accumulators, warp reductions.
-constexpr int NT_OB = 8;
-__global__ void __launch_bounds__(256) linear_nt_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// Long reduction (encoder heads, I = 384): one warp per row keeps the row in registers (NT_XCH values per lane) and walks the
+// outputs; the NT_XCH weight loads of an output are independent and issued together (the first version loaded one weight per
+// loop iteration: a chain of L2 latencies, 12 us at B=32 and 80 us at B=512).
+constexpr int NT_XCH = 12;
+__global__ void __launch_bounds__(128) linear_nt_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y, int R, int I,
                                                         int O) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int ogroups = (O + NT_OB - 1) / NT_OB;
-  const long wid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (wid >= (long)R * ogroups) return;
-  const int r = (int)(wid / ogroups), o0 = (int)(wid % ogroups) * NT_OB;
-  const float* xr = x + (long)r * I;
-  float acc[NT_OB];
+  const long r = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float* xr = x + r * I;
+  for (int o = 0; o < O; ++o) {
+    const float* wr = w + (long)o * I;
+    float acc = 0.f;
+    for (int i0 = 0; i0 < I; i0 += 32 * NT_XCH) {
+      float xv[NT_XCH], wv[NT_XCH];
 #pragma unroll
-  for (int u = 0; u < NT_OB; ++u) acc[u] = 0.f;
-  for (int i = lane; i < I; i += 32) {
-    const float xv = xr[i];
+      for (int k = 0; k < NT_XCH; ++k) {
+        const int i = i0 + lane + 32 * k;
+        xv[k] = i < I ? xr[i] : 0.f;              // L1-resident after the first output
+        wv[k] = i < I ? wr[i] : 0.f;
+      }
 #pragma unroll
-    for (int u = 0; u < NT_OB; ++u)
-      if (o0 + u < O) acc[u] += xv * w[(long)(o0 + u) * I + i];
+      for (int k = 0; k < NT_XCH; ++k) acc = fmaf(xv[k], wv[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) y[r * O + o] = acc + (bias ? bias[o] : 0.f);
   }
+}
+
+// Short reduction, wide output (decoder heads, I = 12 / 24, O = 384): a CTA stages NS_ROWS input rows in shared memory, every thread
+// owns output columns o = tid, tid + 128, ..: it reads its weight row once and produces the column for all staged rows.
+constexpr int NS_ROWS = 8;
+__global__ void __launch_bounds__(128) linear_nt_short_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ y, int R, int I,
+                                                              int O) {
+  extern __shared__ float xs[];                 // [NS_ROWS][I]
+  pdl_trigger();
+  pdl_wait();
+  const long r0 = (long)blockIdx.x * NS_ROWS;
+  const int nr = (R - r0 < NS_ROWS) ? (int)(R - r0) : NS_ROWS;
+  for (int e = threadIdx.x; e < NS_ROWS * I; e += 128) xs[e] = (e / I) < nr ? x[r0 * I + e] : 0.f;
+  __syncthreads();
+  for (int o = threadIdx.x; o < O; o += 128) {
+    const float* wr = w + (long)o * I;
+    float acc[NS_ROWS];
+    const float b = bias ? bias[o] : 0.f;
 #pragma unroll
-  for (int u = 0; u < NT_OB; ++u) {
-    const float v = warp_sum(acc[u]);
-    if (lane == 0 && o0 + u < O) y[(long)r * O + o0 + u] = v + (bias ? bias[o0 + u] : 0.f);
+    for (int q = 0; q < NS_ROWS; ++q) acc[q] = b;
+#pragma unroll 8
+    for (int i = 0; i < I; ++i) {
+      const float wv = wr[i];
+#pragma unroll
+      for (int q = 0; q < NS_ROWS; ++q) acc[q] = fmaf(wv, xs[q * I + i], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NS_ROWS; ++q)
+      if (q < nr) y[(r0 + q) * O + o] = acc[q];
   }
 }
 
@@ -132,8 +166,11 @@ extern "C" int hmvae_linear_fwd(const float* x, const float* w, const float* bia
                                 void* stream) {
   if (!x || !w || !y) return fail_arg("linear_fwd: null pointer");
   if (rows <= 0 || in_f <= 0 || out_f <= 0) return 0;
-  const long warps = (long)rows * ((out_f + NT_OB - 1) / NT_OB);
-  launch_pdl(linear_nt_kernel, dim3((int)((warps + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, x, w, bias, y, rows, in_f, out_f);
+  if (in_f <= 64 && out_f >= 64)
+    launch_pdl(linear_nt_short_kernel, dim3((rows + NS_ROWS - 1) / NS_ROWS), dim3(128), (size_t)NS_ROWS * in_f * sizeof(float),
+               (cudaStream_t)stream, x, w, bias, y, rows, in_f, out_f);
+  else
+    launch_pdl(linear_nt_kernel, dim3((rows + 3) / 4), dim3(128), 0, (cudaStream_t)stream, x, w, bias, y, rows, in_f, out_f);
   return check_launch("linear_fwd");
 }
 

@@ -484,10 +484,18 @@ class TwoHierSAVAEModel(nn.Module):
                 seq_rot_mat = rm.reshape(bs, timesteps, -1)
             seq_rot_pos = self.fk_layer(seq_rot_mat.view(bs * timesteps, self.n_joints, 3, 3))
             gt_seq_res = seq_rot_pos.view(bs, timesteps, 24, 3).transpose(0, 1).contiguous()
-            _, z_vec_list = self.enc(ops.transpose_ct(seq_rot_6d))
+            nl = hp['num_layers']
+            # only the shallow and the deep latent reach the decoder (reference :278-288): the two middle heads are dead work
+            _, z_vec_list = self.enc(ops.transpose_ct(seq_rot_6d), needed={0, nl - 1})
             n = len(z_vec_list)
             mean_z_list, sampled = [], []
             for zi, dist in enumerate(z_vec_list):
+                if dist is None:
+                    if sampled_z_list is None:                       # keep the reference's RNG consumption: one draw per level
+                        torch.randn(bs, len(self.enc.pooling_list[zi]), self.latent_d, device=seq_rot_6d.device)
+                    mean_z_list.append(None)
+                    sampled.append(None)
+                    continue
                 d = self.shallow_latent_d if zi == 0 else self.latent_d
                 mean_z = dist[:, :, :d].contiguous()
                 mean_z_list.append(mean_z)
