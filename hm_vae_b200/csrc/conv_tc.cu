@@ -472,7 +472,7 @@ static void tc_build_layer(const hmvae_conv_plan* plan, int mode, TcLayer* L) {
     const int cols = env_int("HMVAE_TC_DENSE_COLS", 96);
     int gj = cols / np8;
     gj &= ~1;                                        // N = gj * np8 must be a multiple of 16
-    if (want != 0 && np8 <= 16 && gj >= 2 && a.J > L->GJ) {
+    if (want != 0 && np8 <= env_int("HMVAE_TC_DENSE_MAXNP", 16) && gj >= 2 && a.J > L->GJ) {
       long sparse_units = 0, dense_units = 0;
       for (int g = 0; g * L->GJ < a.J; ++g)
         for (int n = 0; n < a.J; ++n) {

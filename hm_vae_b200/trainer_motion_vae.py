@@ -215,7 +215,7 @@ class Trainer(nn.Module):
         host = [i for i, (dst, src) in enumerate(zip(static_in, data)) if dst is not None and torch.is_tensor(src) and not src.is_cuda]
         if not host:
             for dst, src in zip(static_in, data):
-                if dst is not None:
+                if dst is not None and src.data_ptr() != dst.data_ptr():     # the caller may hand back the static buffers themselves
                     dst.copy_(src, non_blocking=True)
             return
         if getattr(self, "_stage", None) is None:
@@ -247,6 +247,11 @@ class Trainer(nn.Module):
         detach = iterations < hp.get('iteration_interval', 0)
         shapes = tuple(tuple(d.shape) if torch.is_tensor(d) else None for d in data)
         return (detach, shapes)
+
+    def static_inputs(self, data, hp, iterations):
+        """The captured step's own input buffers for this batch shape (after ``enable_cuda_graph``): a producer that writes the next
+        batch straight into them (e.g. the on-device batch assembly) and passes them to ``gen_update`` avoids the per-step copy."""
+        return tuple(self._graphs[self._graph_key(hp, iterations, data)][1])
 
     def enable_cuda_graph(self, data, hp, iterations, warmup=3):
         """Captures fwd + bwd (+ all-reduce) + Adam for this batch shape / detach phase.  Inputs are copied into static
