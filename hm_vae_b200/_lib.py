@@ -74,7 +74,7 @@ class ConvLinkDesc(Structure):
 class HeadLevel(Structure):
     _fields_ = [("rows", c_int), ("features", c_int), ("d", c_int), ("kl_scale", c_float), ("x", c_void_p), ("enc_w", c_void_p),
                 ("enc_b", c_void_p), ("eps", c_void_p), ("dec_w", c_void_p), ("dec_b", c_void_p), ("dist", c_void_p), ("z", c_void_p),
-                ("feat", c_void_p), ("kl_acc", c_void_p), ("gfeat", c_void_p), ("gdist", c_void_p), ("gx", c_void_p)]
+                ("feat", c_void_p), ("kl_acc", c_void_p), ("gfeat", c_void_p), ("gdist", c_void_p), ("gx", c_void_p), ("gfeat_stride", c_long)]
 
 
 class RegTensor(Structure):

@@ -37,6 +37,7 @@ struct HeadLevel {
   float* gdist;        // [rows, 2d]
   float* gx;           // [rows, F]
   float kl_scale;      // kl_w / rows
+  long gfeat_stride;   // floats between consecutive rows of gfeat (>= F: the gradient may live inside a wider concat buffer)
   int rows, F, d;
   int cta0;            // first CTA of this level
 };
@@ -158,37 +159,30 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const __grid_cons
   float* gs = hs;                          // [HD_ROWS][F]
   float* gz = gs + HD_ROWS * F;            // [HD_ROWS][d]
   float* gd = gz + HD_ROWS * d;            // [HD_ROWS][2d]
+  float* wds = gd + HD_ROWS * d2;          // [F][d]: the decoder head's weight, staged once per CTA (coalesced) -- read column-wise below
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  (void)lane; (void)warp;
   for (int e = tid; e < HD_ROWS * F; e += HD_THREADS) {
     const int r = e / F;
-    gs[e] = r < nr ? L.gfeat[(size_t)(r0 + r) * F + (e - r * F)] : 0.f;
+    gs[e] = r < nr ? L.gfeat[(size_t)(r0 + r) * L.gfeat_stride + (e - r * F)] : 0.f;
   }
+  for (int e = tid; e < F * d; e += HD_THREADS) wds[e] = L.Wd[e];
   __syncthreads();
-  for (int c = warp; c < d; c += HD_THREADS / 32) {
-    float acc[HD_ROWS];
-#pragma unroll
-    for (int r = 0; r < HD_ROWS; ++r) acc[r] = 0.f;
-    for (int j0 = 0; j0 < F; j0 += 32 * HD_WCH) {
-      float w[HD_WCH];
-#pragma unroll
-      for (int k = 0; k < HD_WCH; ++k) {
-        const int j = j0 + lane + 32 * k;
-        w[k] = j < F ? L.Wd[(size_t)j * d + c] : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < HD_WCH; ++k) {
-        const int j = j0 + lane + 32 * k;
-        if (j < F) {
-#pragma unroll
-          for (int r = 0; r < HD_ROWS; ++r) acc[r] = fmaf(w[k], gs[r * F + j], acc[r]);
-        }
-      }
+  // gz[r][c] = sum_j gfeat[r][j] Wd[j][c]: one thread per (row, c); threads of a warp read consecutive c (conflict-free), the
+  // gfeat element is a broadcast.  (Reading Wd[j*d + c] from global memory, lanes over j, was a strided gather: 34 us per call.)
+  for (int e = tid; e < HD_ROWS * d; e += HD_THREADS) {
+    const int r = e / d, c = e - r * d;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* g = gs + r * F;
+    int jj = 0;
+    for (; jj + 3 < F; jj += 4) {
+      a0 = fmaf(g[jj], wds[jj * d + c], a0);
+      a1 = fmaf(g[jj + 1], wds[(jj + 1) * d + c], a1);
+      a2 = fmaf(g[jj + 2], wds[(jj + 2) * d + c], a2);
+      a3 = fmaf(g[jj + 3], wds[(jj + 3) * d + c], a3);
     }
-#pragma unroll
-    for (int r = 0; r < HD_ROWS; ++r) {
-      const float v = warp_sum(acc[r]);
-      if (lane == 0) gz[r * d + c] = v;
-    }
+    for (; jj < F; ++jj) a0 = fmaf(g[jj], wds[jj * d + c], a0);
+    gz[e] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
   for (int e = tid; e < HD_ROWS * d; e += HD_THREADS) {
@@ -244,10 +238,13 @@ static int heads_pack(const hmvae_head_level* levels, int n, bool bwd, HeadArgs*
     L.x = h.x; L.We = h.enc_w; L.be = h.enc_b; L.eps = h.eps; L.Wd = h.dec_w; L.bd = h.dec_b;
     L.dist = h.dist; L.z = h.z; L.feat = h.feat; L.kl = h.kl_acc;
     L.gfeat = h.gfeat; L.gdist = h.gdist; L.gx = h.gx; L.kl_scale = h.kl_scale;
+    L.gfeat_stride = h.gfeat_stride > 0 ? h.gfeat_stride : h.features;
+    if (L.gfeat_stride < h.features) return fail_arg("latent_heads: gfeat_stride smaller than the row");
     L.rows = h.rows; L.F = h.features; L.d = h.d;
     L.cta0 = cta;
     cta += (h.rows + HD_ROWS - 1) / HD_ROWS;
-    const size_t need = (size_t)HD_ROWS * (h.features + 3 * h.d) * sizeof(float);
+    size_t need = (size_t)HD_ROWS * (h.features + 3 * h.d) * sizeof(float);
+    if (bwd) need += (size_t)h.features * h.d * sizeof(float);
     if (need > sm) sm = need;
   }
   if (sm > 200 * 1024) return fail_arg("latent_heads: feature rows too long for shared memory");

@@ -235,6 +235,7 @@ typedef struct {
   const float* gfeat;
   float* gdist;
   float* gx;
+  long gfeat_stride;   /* floats between consecutive rows of gfeat; 0 = features (contiguous) */
 } hmvae_head_level;
 int hmvae_latent_heads_fwd(const hmvae_head_level* levels, int n_levels, void* stream);
 int hmvae_latent_heads_bwd(const hmvae_head_level* levels, int n_levels, void* stream);
