@@ -404,7 +404,11 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
   // taps per group: L * Nw accumulator columns <= 512
   // accumulator columns per CTA.  Measured: 128 columns (one tap of a 128-column window per CTA => 15x more, shorter CTAs that
   // co-reside with the dgrad kernels of the other stream) beats 256 / 384 / 512: 0.971 / 0.997 / 1.063 / 1.112 ms per step.
-  const int tmem_cap = env_int("HMVAE_WG_TMEM_COLS", 128);
+  // Round 2 (linked stack path, two weight-gradient streams; graph replay of the whole step on one box): 128 columns / 148 target
+  // CTAs 773 us, 256 / 60: 750 us, 384 / 40: 751 us, 512 / 30: 795 us.  A CTA re-loads the dy tile and the x window of every stage
+  // for each tap it owns (ncu: the kernels are bound by that L2 -> shared-memory traffic, 276 MB for the last decoder level with
+  // one tap per CTA), so two taps per CTA halve it -- as long as the position split below does not grow in return.
+  const int tmem_cap = env_int("HMVAE_WG_TMEM_COLS", 256);
   p.Lmax = tmem_cap / p.Nw;
   if (p.Lmax < 1) p.Lmax = 1;
   if (p.Lmax > 16) p.Lmax = 16;                     // epilogue transpose tile: 128 x (16 * L + 1) floats <= 132 KB
@@ -489,7 +493,7 @@ static bool wg_geometry_build(const hmvae_conv_plan* plan, int B, int T, WgArgs*
   {
     // split the (batch group, time window) stages over gridDim.y so that ~one wave of SMs is busy; >= 4 stages per CTA
     const int nst = p.mtiles * p.nwin;
-    int splits = p.nitems > 0 ? env_int("HMVAE_WG_TARGET_CTAS", num_sms()) / p.nitems : 1;
+    int splits = p.nitems > 0 ? env_int("HMVAE_WG_TARGET_CTAS", 60) / p.nitems : 1;
     if (splits > nst / 4) splits = nst / 4;
     if (splits > 8) splits = 8;
     const long dense_bytes = (long)a.J * a.co * a.J * a.ci * a.K * 4;
