@@ -92,14 +92,28 @@ __global__ void __launch_bounds__(128) conv_pack_kernel(ConvArgs a, const float*
   const int blk = blockIdx.x / no4, o4 = blockIdx.x % no4;
   const int j = a.blk_j[blk], n = a.blk_n[blk];
   const TcPk e = pk[blk];
-  for (int i = 0; i < 4; ++i) {
-    const int o = o4 * 4 + i;
-    if (o < a.co) {
-      const float* src = w + ((long)(j * a.co + o) * Cin + n * a.ci) * a.K;
-      for (int x = threadIdx.x; x < run; x += blockDim.x) rows[i * run + x] = __uint_as_float(to_tf32(src[x]));
-    } else {
-      for (int x = threadIdx.x; x < run; x += blockDim.x) rows[i * run + x] = 0.f;
+  // all loads of a pass are issued before the first use: the weights were just rewritten by the optimiser (HBM misses), and a
+  // load -> convert -> store loop walks them one memory latency at a time (the 13.5 MB layers took 21-35 us)
+  constexpr int PK_U = 6;
+  for (int x0 = 0; x0 < run; x0 += PK_U * 128) {
+    float v[4][PK_U];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int o = o4 * 4 + i;
+      const float* src = w + ((long)(j * a.co + (o < a.co ? o : 0)) * Cin + n * a.ci) * a.K;
+#pragma unroll
+      for (int u = 0; u < PK_U; ++u) {
+        const int x = x0 + u * 128 + threadIdx.x;
+        v[i][u] = (o < a.co && x < run) ? src[x] : 0.f;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int u = 0; u < PK_U; ++u) {
+        const int x = x0 + u * 128 + threadIdx.x;
+        if (x < run) rows[i * run + x] = __uint_as_float(to_tf32(v[i][u]));
+      }
   }
   __syncthreads();
   // Thread order follows the DESTINATION's innermost index (o for the fprop copy: 4 x 16 B = 64 contiguous bytes per (tap,
