@@ -670,7 +670,9 @@ def run_b200(args, hp):
                 "vs_baseline": None, "dtype": "tf32" if args.conv_impl != "simt" else "f32", "data": "synthetic",
                 "config": cfg,
                 "run": {"cuda_graph": bool(args.graph), "conv_impl": args.conv_impl, "data_parallel": trainer.dp_mode,
-                        "dp_barrier_timed_out": bool(getattr(trainer.gen_opt, "timed_out", lambda: False)())},
+                        "dp_barrier_timed_out": bool(getattr(trainer.gen_opt, "timed_out", lambda: False)()),
+                        "optimiser_arena_elems": int(getattr(trainer.gen_opt, "numel", 0)),
+                        "optimiser_masked_elems_skipped": int(getattr(trainer.gen_opt, "masked_elems", 0))},
                 "e2e": {"value": world * bs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(h6.numel() * 4 + hm.numel() * 4 + 8), "d2h_bytes_per_step": 20},
                 "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),

@@ -150,6 +150,7 @@ _SIGS = {
     "hmvae_rand_rotation": (c_int, [P, ctypes.c_double, P, c_long, P]),
     "hmvae_batch_assemble": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
     "hmvae_dp_adam_step": (c_int, [POINTER(DpPeers), P, P, POINTER(c_long), c_int, P, c_double, c_double, c_float, c_float, c_float, P, c_int, P]),
+    "hmvae_dp_adam_step_units": (c_int, [POINTER(DpPeers), P, P, P, c_long, P, c_double, c_double, c_float, c_float, c_float, P, c_int, c_int, P]),
     "hmvae_ipc_alloc": (c_int, [c_long, POINTER(c_void_p)]),
     "hmvae_ipc_free": (c_int, [c_void_p]),
     "hmvae_ipc_get_handle": (c_int, [c_void_p, P]),

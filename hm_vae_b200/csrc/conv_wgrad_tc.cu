@@ -567,7 +567,9 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
   unsigned char* xw = dyw + wg_dy_bytes(p);
   {
     const long items = (wg_dy_bytes(p) + wg_x_bytes(p)) / 16;
-    long blocks = (items + 255) / 256, cap = (long)num_sms() * 8;
+    // resident CTAs per SM: the staging pass runs beside the data-gradient chain; a full complement of 8 x 256 threads per SM
+    // leaves the chain's CTAs no thread slots until a staging CTA retires (tools/timeline.py)
+    long blocks = (items + 255) / 256, cap = (long)num_sms() * env_int("HMVAE_WG_PREP_CTAS_PER_SM", 8);
     launch_pdl(conv_wgrad_prep_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, x, dy, yact,
                reinterpret_cast<float4*>(dyw), reinterpret_cast<float4*>(xw));
     int rc = check_launch("conv_wgrad_prep");

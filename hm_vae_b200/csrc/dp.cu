@@ -33,6 +33,8 @@ struct DpArgs {
   unsigned int* flags[HMVAE_DP_MAX_WORLD];      // [2 * world] per rank: entry flags, exit flags (indexed by the SIGNALLING rank)
   long beg[HMVAE_DP_MAX_RANGES], end[HMVAE_DP_MAX_RANGES];   // owned element ranges (multiples of 4, 16-byte aligned)
   int nranges;
+  const int2* units;        // device table of owned work units {first float4, number of float4 (<= 32)}; NULL: the ranges above
+  long nunits;
   const float* mc_grad;     // NVSwitch multicast mappings of the two arenas (NULL: unicast peer loads / stores)
   float* mc_param;
   unsigned long long timeout_ns;
@@ -75,7 +77,12 @@ __device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int
   return true;
 }
 
-template <bool TWO>      // TWO: two float4 per thread and iteration (multi-rank: more peer loads in flight; costs registers)
+// Work is handed out in UNITS of up to 32 consecutive float4 (one per lane): either cut on the fly from the element ranges of
+// the kernel arguments, or read from a device table (the mask-aware path: the table lists only the parameter elements that can
+// ever be non-zero, so the always-masked blocks of the skeleton-conv weights -- 22 % of the arena at len64 -- are never streamed
+// by the reduce-scatter, the optimiser or the all-gather).  U units per warp and iteration = U peer loads in flight per thread
+// (NVLink latency ~2-3 us: a call that runs on few CTAs under the backward pass needs the deeper variant).
+template <int U>
 __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restrict__ m, float* __restrict__ v,
                                                       const float* __restrict__ dyn2, float omb1, float beta2, float omb2, float eps,
                                                       float wd, float gscale, unsigned int* __restrict__ state) {
@@ -100,10 +107,14 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restric
     s_skip = skip;
   }
   __syncthreads();
-  const int nranges = s_skip ? 0 : A.nranges;      // a peer is missing: apply nothing (the host raises at its next health check)
+  const bool table = A.units != nullptr;
+  // a peer is missing: apply nothing (the host raises at its next health check)
+  const int nsets = s_skip ? 0 : (table ? 1 : A.nranges);
   const float lr_over_bc1 = dyn2[0], inv_sqrt_bc2 = dyn2[1];
-  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nthreads = (long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const long gwarp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const bool mc = A.mc_grad != nullptr;
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     gg = gg * gscale + wd * pp;
     mm = mm + (gg - mm) * omb1;
@@ -111,92 +122,74 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restric
     const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
     pp = pp - lr_over_bc1 * (mm / denom);
   };
-  for (int r = 0; r < nranges; ++r) {
-    const long b4 = A.beg[r] >> 2, e4 = A.end[r] >> 2;
-    if (A.mc_grad != nullptr) {
-      // NVSwitch path: the reduce-scatter is one multimem.ld_reduce per element, the all-gather one multimem.st: every rank
-      // moves N/W elements each way instead of N(W-1)/W.
-      for (long i = b4 + tid; i < e4; i += 2 * nthreads) {           // two in-switch reductions in flight per thread
-        const long i2 = i + nthreads;
-        const bool two = i2 < e4;
-        const float4 G = multimem_ld_reduce_add(A.mc_grad + 4 * i);
-        float4 G2 = G;
-        if (two) G2 = multimem_ld_reduce_add(A.mc_grad + 4 * i2);
-        float4 P = reinterpret_cast<const float4*>(A.param[R])[i];
-        float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
-        float4 P2 = P, M2 = M, V2 = V;
-        if (two) {
-          P2 = reinterpret_cast<const float4*>(A.param[R])[i2];
-          M2 = reinterpret_cast<float4*>(m)[i2];
-          V2 = reinterpret_cast<float4*>(v)[i2];
-        }
-        upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
-        reinterpret_cast<float4*>(m)[i] = M;
-        reinterpret_cast<float4*>(v)[i] = V;
-        multimem_st(A.mc_param + 4 * i, P);
-        if (two) {
-          upd(P2.x, G2.x, M2.x, V2.x); upd(P2.y, G2.y, M2.y, V2.y); upd(P2.z, G2.z, M2.z, V2.z); upd(P2.w, G2.w, M2.w, V2.w);
-          reinterpret_cast<float4*>(m)[i2] = M2;
-          reinterpret_cast<float4*>(v)[i2] = V2;
-          multimem_st(A.mc_param + 4 * i2, P2);
-        }
-      }
-      continue;
-    }
-    if constexpr (!TWO) {
-      for (long i = b4 + tid; i < e4; i += nthreads) {
-        float4 G = __ldcg(reinterpret_cast<const float4*>(A.grad[0]) + i);
-        for (int q = 1; q < W; ++q) {
-          const float4 g2 = __ldcg(reinterpret_cast<const float4*>(A.grad[q]) + i);
-          G.x += g2.x; G.y += g2.y; G.z += g2.z; G.w += g2.w;
-        }
-        float4 P = reinterpret_cast<const float4*>(A.param[R])[i];
-        float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
-        upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
-        reinterpret_cast<float4*>(m)[i] = M;
-        reinterpret_cast<float4*>(v)[i] = V;
-        for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(A.param[q])[i] = P;
-      }
-      continue;
-    }
-    // two float4 per thread and iteration: 2 * W peer loads in flight before the first add (NVLink latency ~2-3 us)
-    for (long i = b4 + tid; i < e4; i += (TWO ? 2 : 1) * nthreads) {
-      const long i2 = i + nthreads;
-      const bool two = TWO && i2 < e4;
-      float4 Ga[HMVAE_DP_MAX_WORLD], Gb[HMVAE_DP_MAX_WORLD];
+  const float4* __restrict__ prm = reinterpret_cast<const float4*>(A.param[R]);
+  float4* __restrict__ m4 = reinterpret_cast<float4*>(m);
+  float4* __restrict__ v4 = reinterpret_cast<float4*>(v);
+  for (int r = 0; r < nsets; ++r) {
+    const long b4 = table ? 0 : (A.beg[r] >> 2), e4 = table ? 0 : (A.end[r] >> 2);
+    const long nu = table ? A.nunits : ((e4 - b4 + 31) >> 5);
+    for (long u0 = gwarp; u0 < nu; u0 += (long)U * nwarps) {
+      long idx[U];
+      bool ok[U];
 #pragma unroll
-      for (int q = 0; q < HMVAE_DP_MAX_WORLD; ++q) {
-        if (q < W) {
-          Ga[q] = __ldcg(reinterpret_cast<const float4*>(A.grad[q]) + i);
-          if (two) Gb[q] = __ldcg(reinterpret_cast<const float4*>(A.grad[q]) + i2);
+      for (int k = 0; k < U; ++k) {
+        const long u = u0 + (long)k * nwarps;
+        ok[k] = u < nu;
+        idx[k] = 0;
+        if (ok[k]) {
+          if (table) {
+            const int2 e = __ldg(A.units + u);
+            idx[k] = (long)e.x + lane;
+            ok[k] = lane < e.y;
+          } else {
+            idx[k] = b4 + (u << 5) + lane;
+            ok[k] = idx[k] < e4;
+          }
         }
       }
-      float4 P = reinterpret_cast<const float4*>(A.param[R])[i];
-      float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
-      float4 P2 = P, M2 = M, V2 = V;
-      if (two) {
-        P2 = reinterpret_cast<const float4*>(A.param[R])[i2];
-        M2 = reinterpret_cast<float4*>(m)[i2];
-        V2 = reinterpret_cast<float4*>(v)[i2];
-      }
-      float4 G = Ga[0], G2 = Gb[0];
+      float4 G[U], P[U], M[U], V[U];
+      if (mc) {
+        // NVSwitch path: the reduce-scatter is one multimem.ld_reduce per element, the all-gather one multimem.st: every rank
+        // moves N/W elements each way instead of N(W-1)/W.
 #pragma unroll
-      for (int q = 1; q < HMVAE_DP_MAX_WORLD; ++q) {
-        if (q < W) {                               // fixed order 0..W-1: deterministic
-          G.x += Ga[q].x; G.y += Ga[q].y; G.z += Ga[q].z; G.w += Ga[q].w;
-          if (two) { G2.x += Gb[q].x; G2.y += Gb[q].y; G2.z += Gb[q].z; G2.w += Gb[q].w; }
+        for (int k = 0; k < U; ++k)
+          if (ok[k]) G[k] = multimem_ld_reduce_add(A.mc_grad + 4 * idx[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+          if (ok[k]) G[k] = __ldcg(reinterpret_cast<const float4*>(A.grad[0]) + idx[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (ok[k]) {
+          P[k] = prm[idx[k]];
+          M[k] = m4[idx[k]];
+          V[k] = v4[idx[k]];
+        }
+      if (!mc) {
+        for (int q = 1; q < W; ++q) {                  // fixed order 0..W-1: deterministic; U peer loads in flight per step
+          float4 t[U];
+#pragma unroll
+          for (int k = 0; k < U; ++k)
+            if (ok[k]) t[k] = __ldcg(reinterpret_cast<const float4*>(A.grad[q]) + idx[k]);
+#pragma unroll
+          for (int k = 0; k < U; ++k)
+            if (ok[k]) { G[k].x += t[k].x; G[k].y += t[k].y; G[k].z += t[k].z; G[k].w += t[k].w; }
         }
       }
-      upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
-      reinterpret_cast<float4*>(m)[i] = M;
-      reinterpret_cast<float4*>(v)[i] = V;
-      for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(A.param[q])[i] = P;
-      if (two) {
-        upd(P2.x, G2.x, M2.x, V2.x); upd(P2.y, G2.y, M2.y, V2.y); upd(P2.z, G2.z, M2.z, V2.z); upd(P2.w, G2.w, M2.w, V2.w);
-        reinterpret_cast<float4*>(m)[i2] = M2;
-        reinterpret_cast<float4*>(v)[i2] = V2;
-        for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(A.param[q])[i2] = P2;
-      }
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (ok[k]) {
+          upd(P[k].x, G[k].x, M[k].x, V[k].x); upd(P[k].y, G[k].y, M[k].y, V[k].y);
+          upd(P[k].z, G[k].z, M[k].z, V[k].z); upd(P[k].w, G[k].w, M[k].w, V[k].w);
+          m4[idx[k]] = M[k];
+          v4[idx[k]] = V[k];
+          if (mc) {
+            multimem_st(A.mc_param + 4 * idx[k], P[k]);
+          } else {
+            for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(A.param[q])[idx[k]] = P[k];
+          }
+        }
     }
   }
   __syncthreads();
@@ -222,15 +215,15 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs A, float* __restric
 
 using namespace hmvae;
 
-extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges,
-                                  const float* dyn2, double beta1, double beta2, float eps, float weight_decay,
-                                  float grad_scale, unsigned int* state, int max_ctas, void* stream) {
-  if (!peers || !m || !v || !dyn2 || !state || (nranges > 0 && !ranges)) return fail_arg("dp_adam_step: null pointer");
+static int dp_launch(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges, const int* units,
+                     long nunits, const float* dyn2, double beta1, double beta2, float eps, float weight_decay, float grad_scale,
+                     unsigned int* state, int max_ctas, int in_flight, void* stream) {
+  if (!peers || !m || !v || !dyn2 || !state) return fail_arg("dp_adam_step: null pointer");
   if (peers->world < 1 || peers->world > HMVAE_DP_MAX_WORLD || peers->rank < 0 || peers->rank >= peers->world)
     return fail_arg("dp_adam_step: bad world / rank");
-  if (nranges < 0 || nranges > HMVAE_DP_MAX_RANGES) return fail_arg("dp_adam_step: too many ranges");
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);      // 1 - beta rounded ONCE from double, like torch
   DpArgs A;
+  memset(&A, 0, sizeof(A));
   A.world = peers->world;
   A.rank = peers->rank;
   for (int q = 0; q < HMVAE_DP_MAX_WORLD; ++q) {
@@ -251,25 +244,58 @@ extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* 
     if (secs < 1) secs = 1;
     A.timeout_ns = (unsigned long long)secs * 1000000000ull;
   }
-  long total = 0;
-  A.nranges = nranges;
-  for (int r = 0; r < nranges; ++r) {
-    A.beg[r] = ranges[2 * r];
-    A.end[r] = ranges[2 * r + 1];
-    if (A.beg[r] < 0 || A.end[r] < A.beg[r] || (A.beg[r] & 3) || (A.end[r] & 3)) return fail_arg("dp_adam_step: ranges must be multiples of 4");
-    total += A.end[r] - A.beg[r];
+  long work_units = 0;            // 32-float4 units of this call
+  if (units) {
+    if (nunits < 0 || (reinterpret_cast<uintptr_t>(units) & 7)) return fail_arg("dp_adam_step_units: bad unit table");
+    A.units = nunits > 0 ? reinterpret_cast<const int2*>(units) : nullptr;
+    A.nunits = nunits;
+    A.nranges = 0;
+    work_units = nunits;
+  } else {
+    if (nranges < 0 || nranges > HMVAE_DP_MAX_RANGES) return fail_arg("dp_adam_step: too many ranges");
+    A.nranges = nranges;
+    for (int r = 0; r < nranges; ++r) {
+      A.beg[r] = ranges[2 * r];
+      A.end[r] = ranges[2 * r + 1];
+      if (A.beg[r] < 0 || A.end[r] < A.beg[r] || (A.beg[r] & 3) || (A.end[r] & 3)) return fail_arg("dp_adam_step: ranges must be multiples of 4");
+      work_units += ((A.end[r] - A.beg[r]) / 4 + 31) / 32;
+    }
   }
   // every rank must launch (the flag barriers pair up) even if it owns nothing; all CTAs are resident (<= 4 per SM)
-  long blocks = (total / 4 + 255) / 256;
+  long blocks = (work_units + 7) / 8;
   const long cap = (long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   if (max_ctas > 0 && blocks > max_ctas) blocks = max_ctas;      // a call that runs under other kernels leaves them room
   if (blocks < 1) blocks = 1;
-  if (A.world > 1 && A.mc_grad == nullptr)
-    launch_pdl(dp_adam_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, omb1, (float)beta2, omb2, eps, weight_decay, grad_scale, state);
+  // loads in flight per thread: 1 on one rank (local memory), 2 across ranks, more on request (CTA-capped calls)
+  int U = in_flight > 0 ? in_flight : env_int(A.world > 1 ? "HMVAE_DP_IN_FLIGHT" : "HMVAE_DP_IN_FLIGHT_LOCAL", A.world > 1 ? 2 : 1);
+  const dim3 g((unsigned)blocks), b(256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (U >= 8)
+    launch_pdl(dp_adam_kernel<8>, g, b, 0, st, A, m, v, dyn2, omb1, (float)beta2, omb2, eps, weight_decay, grad_scale, state);
+  else if (U >= 4)
+    launch_pdl(dp_adam_kernel<4>, g, b, 0, st, A, m, v, dyn2, omb1, (float)beta2, omb2, eps, weight_decay, grad_scale, state);
+  else if (U >= 2)
+    launch_pdl(dp_adam_kernel<2>, g, b, 0, st, A, m, v, dyn2, omb1, (float)beta2, omb2, eps, weight_decay, grad_scale, state);
   else
-    launch_pdl(dp_adam_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A, m, v, dyn2, omb1, (float)beta2, omb2, eps, weight_decay, grad_scale, state);
+    launch_pdl(dp_adam_kernel<1>, g, b, 0, st, A, m, v, dyn2, omb1, (float)beta2, omb2, eps, weight_decay, grad_scale, state);
   return check_launch("dp_adam_step");
+}
+
+extern "C" int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges,
+                                  const float* dyn2, double beta1, double beta2, float eps, float weight_decay,
+                                  float grad_scale, unsigned int* state, int max_ctas, void* stream) {
+  if (nranges > 0 && !ranges) return fail_arg("dp_adam_step: null pointer");
+  return dp_launch(peers, m, v, ranges, nranges, nullptr, 0, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state, max_ctas, 0,
+                   stream);
+}
+
+extern "C" int hmvae_dp_adam_step_units(const hmvae_dp_peers* peers, float* m, float* v, const int* units, long nunits,
+                                        const float* dyn2, double beta1, double beta2, float eps, float weight_decay,
+                                        float grad_scale, unsigned int* state, int max_ctas, int loads_in_flight, void* stream) {
+  if (!units) return fail_arg("dp_adam_step_units: null unit table");
+  return dp_launch(peers, m, v, nullptr, 0, units, nunits, dyn2, beta1, beta2, eps, weight_decay, grad_scale, state, max_ctas,
+                   loads_in_flight, stream);
 }
 
 // ---------------------------------------------------------------- peer memory plumbing (CUDA IPC), used when

@@ -61,6 +61,70 @@ def owned_ranges(live, rank, world, total):
     return out
 
 
+UNIT = 32          # float4 per work unit of hmvae_dp_adam_step_units (one per lane of a warp)
+
+
+def mask_live_ranges(mask, offset):
+    """Arena ranges [begin, end) (multiples of ALIGN, merged) covering the non-zero entries of a flattened 0/1 ``mask`` that
+    starts at arena element ``offset`` (itself a multiple of ALIGN).  Rounding outwards may include a few masked elements:
+    they hold zero parameters and zero gradients, on which Adam is the identity."""
+    import numpy as np
+
+    flat = np.asarray(mask).reshape(-1) != 0
+    if flat.size == 0 or not flat.any():
+        return []
+    edges = np.flatnonzero(np.diff(np.concatenate(([False], flat, [False])).astype(np.int8)))
+    begs, ends = edges[0::2], edges[1::2]
+    begs = begs // ALIGN * ALIGN
+    ends = (ends + ALIGN - 1) // ALIGN * ALIGN
+    return merge_ranges([(int(offset + b), int(offset + e)) for b, e in zip(begs, ends)])
+
+
+def balanced_bounds(live, world, total):
+    """W + 1 arena positions that split the LIVE elements of ``live`` (merged ranges) evenly: rank r owns arena elements
+    [bounds[r], bounds[r+1]).  Static (it depends on the masks only), so a rank's slice of the Adam moments never migrates."""
+    live = merge_ranges(live)
+    n4 = sum((e - b) // ALIGN for b, e in live)
+    bounds = [0]
+    for r in range(1, world):
+        want, seen, pos = (n4 * r) // world, 0, total
+        for b, e in live:
+            k = (e - b) // ALIGN
+            if seen + k >= want:
+                pos = b + (want - seen) * ALIGN
+                break
+            seen += k
+        bounds.append(max(pos, bounds[-1]))
+    bounds.append(total)
+    return bounds
+
+
+def clip_ranges(ranges, lo, hi):
+    out = []
+    for b, e in merge_ranges(ranges):
+        s, t = max(b, lo), min(e, hi)
+        if t > s:
+            out.append((s, t))
+    return out
+
+
+def cut_units(ranges):
+    """Merged element ranges -> int32 [n, 2] table {first float4, number of float4 <= UNIT} for hmvae_dp_adam_step_units."""
+    import numpy as np
+
+    firsts, counts = [], []
+    for b, e in ranges:
+        b4, n4 = b // ALIGN, (e - b) // ALIGN
+        starts = np.arange(0, n4, UNIT, dtype=np.int64)
+        firsts.append(b4 + starts)
+        counts.append(np.minimum(UNIT, n4 - starts))
+    if not firsts:
+        return np.zeros((0, 2), dtype=np.int32)
+    out = np.stack([np.concatenate(firsts), np.concatenate(counts)], axis=1)
+    assert out[:, 0].max(initial=0) < 2 ** 31
+    return np.ascontiguousarray(out.astype(np.int32))
+
+
 class _RawCudaBuffer:
     """A device allocation owned by the C library, exposed to torch through __cuda_array_interface__."""
 
@@ -164,7 +228,11 @@ class FusedDataParallelAdam:
     """torch.optim.Adam(lr, betas, eps, weight_decay) over flat peer-mapped arenas; ``step_dyn`` is the fused
     reduce-scatter + Adam + all-gather kernel.  Same host interface as ``ops.FusedAdam`` (advance / step_dyn / zero_grad)."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None, prefer="symm"):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None, prefer="symm", masks=None):
+        """``masks``: {id(parameter): 0/1 tensor of the parameter's shape} for parameters whose masked entries are structurally
+        dead (SkeletonConv.weight / .mask): zero value, zero gradient on every step.  Those entries are left out of the unit
+        table, i.e. never read or written by the step.  A parameter whose masked entries are NOT all zero when the
+        optimiser is built is treated as fully live (weight decay would move them in the reference)."""
         from . import ops
 
         self.params = [p for p in params]
@@ -179,6 +247,22 @@ class FusedDataParallelAdam:
         self.offsets, self.numel = arena_layout([p.numel() for p in self.params])
         self.arenas = PeerArenas(self.numel, dev, group=group, prefer=prefer)
         self.world, self.rank = self.arenas.world, self.arenas.rank
+        # static, mask-aware liveness per parameter and the ranks' (balanced) shares of it
+        self._plive, self.masked_elems = [], 0
+        use_masks = os.environ.get("HMVAE_DP_MASK_AWARE", "1") != "0"
+        for p, off in zip(self.params, self.offsets):
+            n = p.numel()
+            full = [(off, off + (n + ALIGN - 1) // ALIGN * ALIGN)]
+            mk = masks.get(id(p)) if (masks and use_masks) else None
+            if mk is not None and tuple(mk.shape) == tuple(p.shape):
+                mk = mk.detach().to(p.device)
+                if float((p.detach() * (mk == 0)).abs().max()) == 0.0:
+                    rs = mask_live_ranges(mk.cpu().numpy(), off)
+                    self.masked_elems += n - sum(e - b for b, e in rs)
+                    self._plive.append(rs)
+                    continue
+            self._plive.append(full)
+        self.bounds = balanced_bounds([r for rs in self._plive for r in rs], self.world, self.numel)
         self.m = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.v = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.state = torch.zeros(4, device=dev, dtype=torch.int32)
@@ -246,56 +330,69 @@ class FusedDataParallelAdam:
         self.step_count += 1
         self.sched_iters += 1
 
-    def _live_ranges(self, select):
+    def _live_ranges(self, select, written=()):
         """Live = parameters (with index in ``select``) that received a gradient this step.  Gradients that autograd did not
-        place in the arena (it clones a gradient it cannot steal) are copied in."""
-        key, live = [], []
+        place in the arena (it clones a gradient it cannot steal) are copied in.  ``written``: ids of parameters for which the
+        caller vouches that their gradient kernels have been issued and wrote into the arena (a call from INSIDE a backward
+        node, before autograd has assigned ``.grad``)."""
+        key = []
         for i in select:
             p, off = self.params[i], self.offsets[i]
-            if p.grad is None:
+            if p.grad is None and id(p) not in written:
                 continue
             n = p.numel()
-            if p.grad.data_ptr() != self.arenas.grad.data_ptr() + 4 * off:
+            if p.grad is not None and p.grad.data_ptr() != self.arenas.grad.data_ptr() + 4 * off:
                 self.arenas.grad[off:off + n].view(p.shape).copy_(p.grad)
             key.append(i)
             self._live.add(i)
-            live.append((off, off + (n + ALIGN - 1) // ALIGN * ALIGN))
         key = tuple(key)
         if key not in self._range_cache:
-            own = owned_ranges(live, self.rank, self.world, self.numel)
-            if len(own) > _lib.DP_MAX_RANGES:
-                raise _lib.HmvaeError("too many gradient ranges (%d) for hmvae_dp_adam_step" % len(own))
-            flat = (ctypes.c_long * (2 * max(len(own), 1)))()
-            for k, (b, e) in enumerate(own):
-                flat[2 * k], flat[2 * k + 1] = b, e
-            self._range_cache[key] = (flat, len(own), key)
+            if torch.cuda.is_current_stream_capturing():
+                raise _lib.HmvaeError("fused data-parallel step: run one eager step with this set of live parameters before "
+                                      "capturing it in a CUDA graph (the unit table is uploaded on first use)")
+            lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+            own = clip_ranges([r for i in key for r in self._plive[i]], lo, hi)
+            table = cut_units(own)
+            dev_table = torch.from_numpy(table).to(self.arenas.grad.device) if len(table) else \
+                torch.zeros((1, 2), dtype=torch.int32, device=self.arenas.grad.device)
+            self._range_cache[key] = (dev_table, len(table), key)
         return self._range_cache[key]
 
-    def _launch(self, select, grad_scale, max_ctas=0):
+    def _launch(self, select, grad_scale, max_ctas=0, in_flight=0, written=()):
         from . import ops
 
-        flat, n, live = self._live_ranges(select)
+        table, n, live = self._live_ranges(select, written)
         for i in live:
             torch.autograd.graph.increment_version(self.params[i])
         scale = (1.0 / self.world) if grad_scale is None else grad_scale
-        _lib.check(_lib.lib.hmvae_dp_adam_step(ctypes.byref(self._peers), _lib.ptr(self.m), _lib.ptr(self.v), flat, n,
-                                               _lib.ptr(self._dyn_dev), self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                               scale, self.state.data_ptr(), int(max_ctas), ops.stream()), "dp_adam_step")
+        _lib.check(_lib.lib.hmvae_dp_adam_step_units(ctypes.byref(self._peers), _lib.ptr(self.m), _lib.ptr(self.v),
+                                                     table.data_ptr(), n, _lib.ptr(self._dyn_dev), self.betas[0], self.betas[1],
+                                                     self.eps, self.weight_decay, scale, self.state.data_ptr(), int(max_ctas),
+                                                     int(in_flight), ops.stream()), "dp_adam_step_units")
 
     def begin_step(self):
         """Start of a device step (capturable): the device clock ticks and refreshes the step-dependent scalars; nothing has
         been stepped yet."""
         from . import ops
 
-        _lib.check(_lib.lib.hmvae_opt_clock_tick(self._clock.data_ptr(), self.lr, self.gamma, self.step_size, self.betas[0],
-                                                 self.betas[1], _lib.ptr(self._dyn_dev), ops.stream()), "opt_clock_tick")
+        # on the optimiser's side stream: only the optimiser kernels read the scalars, and the first kernels of a step are the
+        # forward pass's critical path
+        if getattr(self, "_opt_stream", None) is None:
+            self._opt_stream = torch.cuda.Stream()
+        self._opt_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._opt_stream):
+            _lib.check(_lib.lib.hmvae_opt_clock_tick(self._clock.data_ptr(), self.lr, self.gamma, self.step_size, self.betas[0],
+                                                     self.betas[1], _lib.ptr(self._dyn_dev), ops.stream()), "opt_clock_tick")
+        self._partial_pending = True           # step_dyn joins the side stream (the tick, and any partial step issued on it)
         self._stepped = set()
         self._begun = True
 
-    def step_partial(self, param_ids, grad_scale=None):
+    def step_partial(self, param_ids, grad_scale=None, written=()):
         """Steps ONLY the given parameters, now, on a side stream: called in the middle of the backward pass as soon as their
-        gradients are final (the decoder's, while the encoder's backward still runs), so that part of the collective + optimiser
-        work hides under the rest of backward.  Every rank must make the same sequence of calls."""
+        gradients are final (the decoder's, while the encoder's backward still runs; the deepest encoder level's, while the
+        shallower levels' backward still runs), so that the collective + optimiser work of each bucket hides under the rest of
+        backward -- buckets in reverse-layer order.  Every rank must make the same sequence of calls.  ``written``: see
+        ``_live_ranges``."""
         from . import ops
 
         if not getattr(self, "_begun", False):
@@ -310,7 +407,8 @@ class FusedDataParallelAdam:
         for s in ops._overlap.get("used", ()) or ():           # weight gradients are produced on the side stream(s)
             self._opt_stream.wait_stream(s)
         with torch.cuda.stream(self._opt_stream):
-            self._launch(select, grad_scale, max_ctas=int(os.environ.get("HMVAE_DP_PARTIAL_CTAS", "296")))
+            self._launch(select, grad_scale, max_ctas=int(os.environ.get("HMVAE_DP_PARTIAL_CTAS", "296")),
+                         in_flight=int(os.environ.get("HMVAE_DP_PARTIAL_IN_FLIGHT", "0")), written=written)
         self._stepped.update(select)
         self._partial_pending = True
 
@@ -342,7 +440,7 @@ class FusedDataParallelAdam:
     # ---- checkpoints: every rank only maintains the moments of its static share of the arena
     def _full_moments(self):
         """COLLECTIVE over ``self.group`` when world > 1: every rank must call it."""
-        lo, hi = rank_share(self.numel, self.rank, self.world)
+        lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         m, v = torch.zeros_like(self.m), torch.zeros_like(self.v)
         m[lo:hi] = self.m[lo:hi]
         v[lo:hi] = self.v[lo:hi]

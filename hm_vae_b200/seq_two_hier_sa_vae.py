@@ -13,6 +13,8 @@ What differs is how a step executes:
   * Loss values stay on the device; nothing in here synchronises with the host.
 """
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -290,30 +292,43 @@ class TwoHierSAVAEModel(nn.Module):
         k_edges = [len(p) for p in self.enc.pooling_list]
         lat = [self.shallow_latent_d] + [self.latent_d] * (n - 1)
         eps, eps_ready = [None] * n, None
+        draw = None                            # deferred draw: () -> (eps, ready event); called once, after the encoder is issued
         if hp['kl_w'] != 0:
             if eps_list is not None:
                 eps = self._draw_eps(None, dev, eps_list)
             else:
-                # the four N(0,1) draws depend on nothing: issue them on the side stream, off the encoder's critical path
-                side, main = ops._eps_stream(), torch.cuda.current_stream()
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    eps = self._draw_eps([(bs * k_edges[i], lat[i]) for i in range(n)], dev, None)
-                    eps_ready = torch.cuda.Event()
-                    eps_ready.record()
-                for e in eps:
-                    e.record_stream(main)
+                # The four N(0,1) draws depend on nothing: they run on a side stream that forks HERE, off the encoder's critical
+                # path -- but they are ISSUED only after the encoder's kernels: a replayed CUDA graph hands its first nodes to
+                # the GPU one after the other (~2 us each, tools/timeline.py), and four generator kernels ahead of the first
+                # conv delayed it by as much.
+                fork = torch.cuda.Event()
+                fork.record()
+
+                def draw(_main=torch.cuda.current_stream()):
+                    side = ops._eps_stream()
+                    side.wait_event(fork)
+                    with torch.cuda.stream(side):
+                        e = self._draw_eps([(bs * k_edges[i], lat[i]) for i in range(n)], dev, None)
+                        ready = torch.cuda.Event()
+                        ready.record()
+                    for t in e:
+                        t.record_stream(_main)
+                    return e, ready
+                if os.environ.get("HMVAE_LATE_EPS", "1") == "0":
+                    (eps, eps_ready), draw = draw(), None
+        late = {"eps": eps, "ready": eps_ready, "draw": draw}
         ops.prefetch_packs(self.enc.conv_plans() + self.dec.conv_plans())   # tf32 weight copies, on the side stream
         x = ops.transpose_ct(seq_rot_6d)                            # bs X (24*6) X T   (input is [B, T, C])
         # persistent accumulators: [sum sq 6d, sum sq rot, sum sq pos, unused, KL sum shallow, KL sum deep]; zeroed by finalize
         acc, res = self._loss_buffers(dev)
         split = self.mid_backward is not None and not validation_flag
-        out = self._fused_bottleneck(x, eps, eps_ready, acc, hp, detach_shallow, split) if n > 1 else None
+        out = self._fused_bottleneck(x, late, acc, hp, detach_shallow, split) if n > 1 else None
         fused = out is not None
         if fused:
             out, enc_outs, enc_cut = out
         else:
             _, z_vec_list = self.enc(x, needed={0, n - 1})
+            eps, eps_ready = self._eps_now(late)
             if eps_ready is not None:
                 torch.cuda.current_stream().wait_event(eps_ready)
             z_list = [None] * n
@@ -367,7 +382,14 @@ class TwoHierSAVAEModel(nn.Module):
 
         return l_total, l_kl, l_rec_6d, l_rec_rot_mat, l_rec_pose, zero, zero, zero, zero, l_kl_list
 
-    def _fused_bottleneck(self, x, eps, eps_ready, acc, hp, detach_shallow, split):
+    @staticmethod
+    def _eps_now(late):
+        """Issues the deferred N(0,1) draws (once)."""
+        if late["draw"] is not None:
+            (late["eps"], late["ready"]), late["draw"] = late["draw"](), None
+        return late["eps"], late["ready"]
+
+    def _fused_bottleneck(self, x, late, acc, hp, detach_shallow, split):
         """Encoder stack -> both latent heads + reparametrisation + KL + both decoder heads in one kernel -> decoder stack (the
         linked tensor-core path, stack.py).  Returns (decoder output, encoder outputs fed to the heads, their detached twins when
         ``split``) or None when the linked path cannot run this geometry (caller takes the per-layer path)."""
@@ -381,6 +403,7 @@ class TwoHierSAVAEModel(nn.Module):
             return None
         bs = x.shape[0]
         k_edges = [len(p) for p in enc.pooling_list]
+        eps, eps_ready = self._eps_now(late)
         if eps_ready is not None:
             torch.cuda.current_stream().wait_event(eps_ready)
         srcs = [outs[0], outs[n - 1]]                       # shallow (level 0) and deep (level n-1) features

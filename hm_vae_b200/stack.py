@@ -14,6 +14,7 @@ path (returns None from ``*_forward``) when a geometry is not supported by the t
 """
 import contextlib
 import ctypes
+import os
 import weakref
 
 import torch
@@ -107,12 +108,14 @@ class _Geometry:
             self.t_out.append(t)
 
 
-def _wgrad(plan, x, gy, y, w, bias, b, t_in, want_w, want_b):
-    """Weight / bias gradient of one conv on the side stream (inside ops.wgrad_overlap) -- same kernels as the per-layer path."""
+def _wgrad(plan, x, gy, y, w, bias, b, t_in, want_w, want_b, inline=False):
+    """Weight / bias gradient of one conv on the side stream (inside ops.wgrad_overlap) -- same kernels as the per-layer path.
+    ``inline``: on the caller's stream instead (the LAST weight gradient of a backward pass: nothing is left to overlap with, and
+    round-robin would queue it behind an earlier layer's kernels on a side stream)."""
     if not (want_w or want_b):
         return None, None
     side = None
-    if ops._overlap["on"]:
+    if ops._overlap["on"] and not inline:
         side = ops._wgrad_stream()
         side.wait_stream(torch.cuda.current_stream())
     with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
@@ -195,15 +198,22 @@ class _DecoderStackFn(Function):
         gws, gbs = [None] * n, [None] * n
         gbounds = [None] * (n + 1)
         gbounds[n] = gout
-        # the last conv's weight gradient needs nothing from the dgrad chain: issue it first
-        gws[n - 1], gbs[n - 1] = _wgrad(plans[n - 1], bounds[n - 1], gout, bounds[n] if plans[n - 1].lrelu else None, ws[n - 1], bs[n - 1],
-                                        b, geo.t_in[n - 1], need_w[n - 1], need_b[n - 1])
-        if need_x or any(need_w[:-1]) or any(need_b[:-1]):
+        # the last conv's weight gradient needs nothing from the dgrad chain.  Issued AFTER the chain's first two kernels: nodes of a
+        # replayed graph that become ready together are dispatched in issue order, and the staging pass of this weight gradient
+        # fills every SM's thread slots for ~30 us (tools/timeline.py: the first dgrad kernel started 10 us late behind it)
+        chain = need_x or any(need_w[:-1]) or any(need_b[:-1])
+        first = lambda: _wgrad(plans[n - 1], bounds[n - 1], gout, bounds[n] if plans[n - 1].lrelu else None, ws[n - 1], bs[n - 1],
+                               b, geo.t_in[n - 1], need_w[n - 1], need_b[n - 1])
+        if not (chain and _wgrad_after_dgrad):
+            gws[n - 1], gbs[n - 1] = first()
+        if chain:
             st, dump = _bufs(plans[n - 1], 1, b, geo.t_in[n - 1])
             check(lib.hmvae_conv_tc_stage(plans[n - 1].handle, 1, ptr(gout), ptr(bounds[n]) if plans[n - 1].lrelu else None, b,
                                           geo.t_in[n - 1], ptr(st), stream()), "conv_tc_stage")
             check(lib.hmvae_conv_tc_run(plans[n - 1].handle, 1, ptr(ctx.packs_d[n - 1]), b, geo.t_in[n - 1], ptr(st), ptr(dump), stream()),
                   "conv_tc_run")
+            if _wgrad_after_dgrad:
+                gws[n - 1], gbs[n - 1] = first()
             for i in range(n - 1, -1, -1):
                 prod = plans[i]
                 cons = plans[i - 1] if i > 0 else None
@@ -280,6 +290,14 @@ def decoder_forward(dec, feat0, feat_last):
 
 
 # ======================================================================================================== encoder
+# encoder module -> optional callback(layer, n_layers), called from inside that encoder stack's backward right after the weight /
+# bias gradient kernels of ``layer`` have been issued (they write into the registered gradient buffers): lets the optimiser start
+# on that bucket while the shallower levels' backward still runs
+wgrad_issued_hooks = weakref.WeakKeyDictionary()
+_last_inline = os.environ.get("HMVAE_WGRAD_LAST_INLINE", "1") != "0"
+_wgrad_after_dgrad = os.environ.get("HMVAE_WGRAD_AFTER_DGRAD", "1") != "0"
+
+
 class _EncoderStackFn(Function):
     @staticmethod
     def forward(ctx, spec, x, *params):
@@ -353,13 +371,22 @@ class _EncoderStackFn(Function):
         staged = False
         for i in range(top, -1, -1):
             plan = plans[i]
-            gws[i], gbs[i] = _wgrad(plan, bounds[i], gy, yact, ws[i], bs[i], b, geo.t_in[i], need_w[i], need_b[i])
+
+            def wgrad_i(i=i, plan=plan, gy=gy, yact=yact):
+                gws[i], gbs[i] = _wgrad(plan, bounds[i], gy, yact, ws[i], bs[i], b, geo.t_in[i], need_w[i], need_b[i],
+                                        inline=(i == 0 and _last_inline))
+                if spec.get("hook") is not None:
+                    spec["hook"](i, n)                     # e.g. the optimiser's bucket for this level (Trainer, split step)
+            if i == 0 or not _wgrad_after_dgrad:
+                wgrad_i()
             if i == 0:
                 break                                      # the network input has no gradient: conv 0 needs no dgrad
             st, dump = _bufs(plan, 1, b, geo.t_in[i])
             if not staged:
                 check(lib.hmvae_conv_tc_stage(plan.handle, 1, ptr(gy), ptr(yact), b, geo.t_in[i], ptr(st), stream()), "conv_tc_stage")
             check(lib.hmvae_conv_tc_run(plan.handle, 1, ptr(ctx.packs_d[i]), b, geo.t_in[i], ptr(st), ptr(dump), stream()), "conv_tc_run")
+            if _wgrad_after_dgrad:
+                wgrad_i()                                  # after the chain's kernel of this level (issue order = dispatch order)
             prev = plans[i - 1]
             cons = prev if i - 1 >= 1 else None
             gy_prev = torch.empty((b, prev.joints * prev.co, geo.t_out[i - 1]), device=dev, dtype=torch.float32)
@@ -413,7 +440,7 @@ def encoder_forward(enc, x, needed=None):
     spec = encoder_spec(enc, x.shape[0], x.shape[2])
     if spec is None:
         return None
-    spec = dict(spec, needed=set(range(len(enc.convs))) if needed is None else set(needed))
+    spec = dict(spec, needed=set(range(len(enc.convs))) if needed is None else set(needed), hook=wgrad_issued_hooks.get(enc))
     ws = [c.weight for c in enc.convs]
     bs = [c.bias for c in enc.convs]
     return _EncoderStackFn.apply(spec, x, *ws, *bs)

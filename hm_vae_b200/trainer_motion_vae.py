@@ -108,8 +108,12 @@ class Trainer(nn.Module):
             if fused:
                 try:
                     from .dp_fused import FusedDataParallelAdam
+                    from .skeleton import SkeletonConv
+                    # structurally dead weight entries (skeleton.py:84-96: zero at init, multiplied by the mask in forward):
+                    # the fused step leaves them out of its reduce-scatter / Adam / all-gather sweep
+                    masks = {id(mod.weight): mod.mask for mod in self.model.modules() if isinstance(mod, SkeletonConv)}
                     self.gen_opt = FusedDataParallelAdam(params, lr=self.base_lr, weight_decay=self.cfg['weight_decay'],
-                                                         prefer=os.environ.get("HMVAE_DP_PEER", "symm"))
+                                                         prefer=os.environ.get("HMVAE_DP_PEER", "symm"), masks=masks)
                     self._configure_schedule()
                     self._sync = _NoCollective(world)
                     self.dp_mode = "fused_peer_memory(%s)" % self.gen_opt.arenas.backend
@@ -123,6 +127,25 @@ class Trainer(nn.Module):
                         dec_ids = {id(p) for p in dec.parameters()} - enc_ids
                         self.model.mid_backward = lambda: self.gen_opt.step_partial(dec_ids, grad_scale=1.0 / world)
                         self.dp_mode += "+split"
+                        # second bucket (reverse-layer order): the deepest encoder conv -- a quarter of the arena at len64 -- and
+                        # the encoder's latent heads, as soon as that level's weight-gradient kernels have been issued; the
+                        # step's tail then only covers the shallow encoder levels
+                        if os.environ.get("HMVAE_DP_SPLIT_ENC", "1") != "0" and hasattr(self.model.enc, "convs"):
+                            import weakref
+                            from . import stack
+                            convs = list(self.model.enc.convs)
+                            conv_ids = {id(p) for c in convs for p in c.parameters()}
+                            top_ids = {id(p) for p in convs[-1].parameters() if p.requires_grad}
+                            bucket_ids = top_ids | (enc_ids - conv_ids)
+                            me = weakref.ref(self)
+
+                            def _bucket(layer, n_layers):
+                                tr = me()
+                                if tr is not None and tr.gen_opt is not None and layer == n_layers - 1:
+                                    # the conv's .grad is assigned only when the stack's backward node returns: vouch for it
+                                    tr.gen_opt.step_partial(bucket_ids, grad_scale=1.0 / world, written=top_ids)
+                            stack.wgrad_issued_hooks[self.model.enc] = _bucket
+                            self.dp_mode += "2"
                     return
                 except ops._lib.HmvaeError as exc:
                     if self._dp_fused:

@@ -360,6 +360,17 @@ typedef struct {
 int hmvae_dp_adam_step(const hmvae_dp_peers* peers, float* m, float* v, const long* ranges, int nranges, const float* dyn2,
                        double beta1, double beta2, float eps, float weight_decay, float grad_scale, unsigned int* state,
                        int max_ctas, void* stream);
+/* Same step over a DEVICE table of work units instead of host ranges -- the mask-aware variant: the masked
+ * (joint, non-neighbour joint) blocks of a SkeletonConv weight are zero at initialisation (skeleton.py:84-93) and receive a
+ * zero gradient on every step (the forward multiplies by the mask, skeleton.py:96), so torch.optim.Adam never moves them; the
+ * table simply does not list them and neither the reduce-scatter, the optimiser nor the all-gather streams those bytes.
+ *   units : device int32 [nunits][2] = {first float4 of the unit, number of float4 (1..32)}, owned by THIS rank, pairwise
+ *           disjoint over all ranks (one warp handles one unit per step; 8-byte aligned).
+ *   loads_in_flight : units per warp and iteration (1, 2, 4 or 8; 0 = default: 1 on one rank, 2 across ranks).  A call capped
+ *           to few CTAs hides the NVLink latency with more loads per thread instead of more threads. */
+int hmvae_dp_adam_step_units(const hmvae_dp_peers* peers, float* m, float* v, const int* units, long nunits, const float* dyn2,
+                             double beta1, double beta2, float eps, float weight_decay, float grad_scale, unsigned int* state,
+                             int max_ctas, int loads_in_flight, void* stream);
 /* Peer-memory plumbing over CUDA IPC (used when torch's symmetric memory is unavailable): zero-filled device allocation, its
  * 64-byte handle, and mapping / unmapping of another process's handle. */
 int hmvae_ipc_alloc(long bytes, void** ptr);

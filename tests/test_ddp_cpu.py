@@ -112,6 +112,53 @@ def test_arena_layout_and_static_ownership():
         assert sum(e - b for b, e in covered) == sum(e - b for b, e in merge_ranges(live))   # ... and disjoint
 
 
+def test_mask_aware_unit_tables():
+    """Host logic of the mask-aware fused step (hmvae_dp_adam_step_units): live ranges of a SkeletonConv mask, the ranks'
+    balanced static shares and the unit tables -- over all ranks the units cover every unmasked element exactly once and
+    (apart from the <= 3 elements of outward rounding per run) nothing else."""
+    import numpy as np
+
+    from hm_vae_b200.dp_fused import ALIGN, UNIT, arena_layout, balanced_bounds, clip_ranges, cut_units, mask_live_ranges
+    from hm_vae_b200.skeleton import SkeletonConv, find_neighbor, get_edges
+    import os as _os
+    d = np.load(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "hm_vae_b200", "data", "smpl24.npz"))
+    parents = d["parents"].tolist()
+    edges = get_edges(parents)
+    nb = find_neighbor(edges, 2)
+    conv = SkeletonConv(nb, 6 * len(nb), 12 * len(nb), 15, len(nb), padding=7, padding_mode='reflection')
+    mask = conv.mask.detach().numpy()
+    numels = [mask.size, 12 * len(nb), 7, 24 * 384]
+    offs, total = arena_layout(numels)
+    plive = [mask_live_ranges(mask, offs[0])] + [[(o, o + (n + ALIGN - 1) // ALIGN * ALIGN)] for o, n in zip(offs[1:], numels[1:])]
+    flat = mask.reshape(-1) != 0
+    cover = np.zeros(total, dtype=np.int32)
+    for b, e in plive[0]:
+        assert b % ALIGN == 0 and e % ALIGN == 0
+        cover[b:e] += 1
+    assert cover.max() == 1 and (cover[offs[0]:offs[0] + mask.size][flat] == 1).all()
+    runs = len(plive[0])
+    assert cover.sum() - flat.sum() <= 2 * (ALIGN - 1) * runs and cover.sum() < 0.9 * mask.size      # most masked entries are skipped
+    assert mask_live_ranges(np.zeros((4, 4)), 0) == [] and mask_live_ranges(np.ones((2, 6)), 8) == [(8, 20)]
+    all_live = [r for rs in plive for r in rs]
+    n_live = sum(e - b for b, e in all_live)
+    for world in (1, 2, 3, 8):
+        bounds = balanced_bounds(all_live, world, total)
+        assert bounds[0] == 0 and bounds[-1] == total and all(bounds[i] <= bounds[i + 1] and bounds[i] % ALIGN == 0 for i in range(world))
+        seen = np.zeros(total, dtype=np.int32)
+        for r in range(world):
+            own = clip_ranges(all_live, bounds[r], bounds[r + 1])
+            assert abs(sum(e - b for b, e in own) - n_live / world) <= ALIGN             # balanced on LIVE elements
+            table = cut_units(own)
+            assert table.dtype == np.int32 and table.shape[1] == 2 and (table[:, 1] >= 1).all() and (table[:, 1] <= UNIT).all()
+            for f, n in table:
+                seen[ALIGN * f:ALIGN * (f + n)] += 1
+        want = np.zeros(total, dtype=np.int32)
+        for b, e in all_live:
+            want[b:e] = 1
+        assert (seen == want).all()
+    assert cut_units([]).shape == (0, 2)
+
+
 def _dp_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)

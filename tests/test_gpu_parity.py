@@ -531,6 +531,59 @@ def test_dp_adam_kernel_vs_torch_single_rank():
     ops.unregister_grad_buffers()
 
 
+def test_dp_adam_mask_aware_units_vs_torch():
+    """The mask-aware unit table (hmvae_dp_adam_step_units): structurally dead entries of a SkeletonConv-style
+    weight are left out of the sweep.  Against torch.optim.Adam with weight decay on the dense tensors: identical parameters and
+    moments on the live entries; dead entries stay exactly zero and are NEVER read (garbage planted in their gradient slots is
+    ignored) nor written (moments stay zero).  A tensor whose masked entries are not zero at construction stays fully live."""
+    from hm_vae_b200.dp_fused import FusedDataParallelAdam
+
+    gen = torch.Generator().manual_seed(9)
+    shapes = [(48, 24, 15), (48,), (40, 30, 3), (7,)]
+    mask0 = torch.zeros(shapes[0])
+    for j in range(8):                                   # 8 joints x 6 out-channels, neighbours j-1..j+1 (3 in-channels each)
+        lo, hi = max(0, j - 1) * 3, min(8, j + 2) * 3
+        mask0[6 * j:6 * j + 6, lo:hi, :] = 1
+    mask2 = (torch.rand(shapes[2], generator=gen) > 0.5).float()
+    ps = [torch.randn(*s, generator=gen) for s in shapes]
+    ps[0] = ps[0] * mask0                                # dead entries zero, as SkeletonConv.reset_parameters leaves them
+    ref_p = [p.clone().requires_grad_(True) for p in ps]
+    opt_ref = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=1e-2)
+    mine_p = [torch.nn.Parameter(p.clone().to(DEV)) for p in ps]
+    opt = FusedDataParallelAdam(mine_p, lr=1e-3, weight_decay=1e-2,
+                                masks={id(mine_p[0]): mask0.to(DEV), id(mine_p[2]): mask2.to(DEV)})
+    covered = torch.zeros(mask0.numel(), dtype=torch.bool)     # live runs are rounded outwards to 16 bytes: a few dead neighbours
+    for b, e in opt._plive[0]:                                 # (zero value, zero gradient) ride along
+        covered[b - opt.offsets[0]:e - opt.offsets[0]] = True
+    covered = covered.view(mask0.shape)
+    assert bool(covered[mask0 != 0].all()) and opt.masked_elems == int((~covered).sum()) > 0.8 * int((mask0 == 0).sum())
+    assert opt._plive[2] == [(opt.offsets[2], opt.offsets[2] + 40 * 30 * 3)]          # non-zero masked entries: fully live
+    for step in range(3):
+        gs = [torch.randn(*s, generator=gen) for s in shapes]
+        gs[0] = gs[0] * mask0
+        for p, g in zip(ref_p, gs):
+            p.grad = g.clone()
+        for i, (p, g) in enumerate(zip(mine_p, gs)):
+            buf = ops.grad_buffer(p)
+            buf.copy_(g.to(DEV))
+            if i == 0:
+                buf[(~covered).to(DEV)] = 123.0          # never read
+            p.grad = buf
+        opt_ref.step()
+        opt.step()
+    assert not opt.timed_out()
+    for a, b in zip(mine_p, ref_p):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-7)
+    assert float(mine_p[0].detach().cpu()[mask0 == 0].abs().max()) == 0.0
+    sd = opt.state_dict()
+    assert float(sd["state"][0]["exp_avg"].cpu()[~covered].abs().max()) == 0.0           # ... nor written
+    for i in range(4):
+        live = mask0 != 0 if i == 0 else torch.ones(shapes[i], dtype=torch.bool)
+        for key in ("exp_avg", "exp_avg_sq"):
+            np.testing.assert_allclose(sd["state"][i][key].cpu()[live].numpy(), opt_ref.state[ref_p[i]][key][live].numpy(), rtol=1e-4, atol=1e-6)
+    ops.unregister_grad_buffers()
+
+
 def test_trainer_fused_dp_matches_plain_step(smpl):
     """Three optimisation steps of the len8 model through Trainer with the fused arena optimiser (forced on one GPU) and with
     the multi-tensor Adam: same losses, same parameters (the gradient kernels write straight into the arena)."""

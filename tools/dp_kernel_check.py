@@ -40,16 +40,24 @@ def rel_l2(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
 
+# tensor 0 is a SkeletonConv-style weight (24 joints x 12 output / 6 input channels, banded neighbourhood): its masked entries
+# are structurally dead (zero value, zero gradient) and left out of the sweep by the mask-aware unit table
+MASK0 = torch.zeros(shapes[0])
+for j in range(24):
+    MASK0[12 * j:12 * j + 12, max(0, j - 2) * 6:min(24, j + 3) * 6, :] = 1
 gen = torch.Generator().manual_seed(7)
 init = [torch.randn(*s, generator=gen) for s in shapes]
+init[0] = init[0] * MASK0
 mine = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
-opt = FusedDataParallelAdam(mine, lr=LR, weight_decay=WD)
+opt = FusedDataParallelAdam(mine, lr=LR, weight_decay=WD, masks={id(mine[0]): MASK0.to(dev)})
+assert opt.masked_elems > 0.7 * int((MASK0 == 0).sum()) or os.environ.get("HMVAE_DP_MASK_AWARE", "1") == "0"
 ref_p = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
 ref = torch.optim.Adam(ref_p, lr=LR, betas=(B1, B2), weight_decay=WD)
 fails = []
 for step in range(1, 4):
     g = torch.Generator().manual_seed(1000 * step + rank)
     grads = [torch.randn(*s, generator=g).to(dev) for s in shapes]
+    grads[0] = grads[0] * MASK0.to(dev)
     for i, (p, gr) in enumerate(zip(mine, grads)):
         if i == DEAD:
             p.grad = None
