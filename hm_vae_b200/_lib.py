@@ -117,6 +117,7 @@ _SIGS = {
     "hmvae_conv_wgrad_tc_supported": (c_int, [P, c_int, c_int]),
     "hmvae_conv_wgrad_tc_workspace": (c_long, [P, c_int, c_int]),
     "hmvae_conv_wgrad_tc": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, c_long, P]),
+    "hmvae_conv_wgrad_tc_stage_x": (c_int, [P, P, c_int, c_int, P, c_long, P]),
     "hmvae_pool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, IP, IP, c_int, P]),
     "hmvae_pool_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, IP, IP, c_int, P]),
     "hmvae_unpool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, IP, P]),

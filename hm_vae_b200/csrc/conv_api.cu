@@ -50,6 +50,8 @@ int conv_tc_finish(const hmvae_conv_plan* plan, int mode, const void* dump_ws, c
 void conv_tc_release(const hmvae_conv_plan* plan);
 bool conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int B, int T);
 long conv_wgrad_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T);
+int conv_wgrad_tc_stage_x(const hmvae_conv_plan* plan, const float* x, int B, int T, void* workspace, long workspace_bytes,
+                          cudaStream_t st);
 int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* yact, float* dw,
                          float* dbias, int B, int T, int accumulate, void* workspace, long workspace_bytes, cudaStream_t st);
 }  // namespace hmvae
@@ -270,7 +272,16 @@ extern "C" int hmvae_conv_wgrad_tc(const hmvae_conv_plan* plan, const float* x, 
                                    void* stream) {
   int rc = check_shape(plan, batch, t_in, "conv_wgrad_tc");
   if (rc) return rc;
-  if (!x || !dy || !dw || (plan->d.lrelu && !y)) return fail_arg("conv_wgrad_tc: null pointer");
+  if (!dy || !dw || (plan->d.lrelu && !y)) return fail_arg("conv_wgrad_tc: null pointer");      // x == NULL: pre-staged
   if (batch == 0) return 0;
   return conv_wgrad_tc_launch(plan, x, dy, y, dw, dbias, batch, t_in, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int hmvae_conv_wgrad_tc_stage_x(const hmvae_conv_plan* plan, const float* x, int batch, int t_in, void* workspace,
+                                           long workspace_bytes, void* stream) {
+  int rc = check_shape(plan, batch, t_in, "conv_wgrad_tc_stage_x");
+  if (rc) return rc;
+  if (!x) return fail_arg("conv_wgrad_tc_stage_x: null pointer");
+  if (batch == 0) return 0;
+  return conv_wgrad_tc_stage_x(plan, x, batch, t_in, workspace, workspace_bytes, (cudaStream_t)stream);
 }

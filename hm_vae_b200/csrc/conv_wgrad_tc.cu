@@ -88,7 +88,7 @@ __device__ __host__ __forceinline__ void wg_window(int s, int k0, int L, int pha
 //                                            input index (stride 1: padded coordinate; stride 2: index inside the phase)
 __global__ void __launch_bounds__(256) conv_wgrad_prep_kernel(WgArgs p, const float* __restrict__ x,
                                                               const float* __restrict__ dy, const float* __restrict__ yact,
-                                                              float4* __restrict__ dyw, float4* __restrict__ xw) {
+                                                              float4* __restrict__ dyw, float4* __restrict__ xw, int part) {
   pdl_trigger();
   pdl_wait();
   const ConvArgs& a = p.a;
@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_prep_kernel(WgArgs p, const fl
   const long n_x = (long)nst * p.nwinN * p.nphase * (p.RxAll / 4) * p.Nw;
   const int Tq = p.T + 2 * a.p;
   const int bq = p.Bt / 4;
-  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < n_dy + n_x; it += (long)gridDim.x * blockDim.x) {
+  // part 0: both operands; 1: dy only (x was staged ahead of time, during the forward pass); 2: x only
+  const long it_lo = (part == 2) ? n_dy : 0, it_hi = (part == 1) ? n_dy : n_dy + n_x;
+  for (long it = it_lo + (long)blockIdx.x * blockDim.x + threadIdx.x; it < it_hi; it += (long)gridDim.x * blockDim.x) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (it < n_dy) {
       // thread order: time fastest inside (row, b-quad) so that the 4 scalar loads of neighbouring threads coalesce along t
@@ -556,6 +558,30 @@ long conv_wgrad_tc_workspace_bytes(const hmvae_conv_plan* plan, int B, int T) {
   return wg_dy_bytes(p) + wg_x_bytes(p) + wg_part_bytes(p);
 }
 
+// staging pass: part 0 = both operands, 1 = dy only, 2 = x only (see conv_wgrad_prep_kernel)
+static int wg_stage(const WgArgs& p, const float* x, const float* dy, const float* yact, unsigned char* dyw, unsigned char* xw,
+                    int part, cudaStream_t st) {
+  const long items = ((part == 2 ? 0 : wg_dy_bytes(p)) + (part == 1 ? 0 : wg_x_bytes(p))) / 16;
+  // resident CTAs per SM: the staging pass runs beside the data-gradient chain; a full complement of 8 x 256 threads per SM
+  // leaves the chain's CTAs no thread slots until a staging CTA retires (tools/timeline.py)
+  long blocks = (items + 255) / 256, cap = (long)num_sms() * env_int("HMVAE_WG_PREP_CTAS_PER_SM", 8);
+  launch_pdl(conv_wgrad_prep_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, x, dy, yact,
+             reinterpret_cast<float4*>(dyw), reinterpret_cast<float4*>(xw), part);
+  return check_launch("conv_wgrad_prep");
+}
+
+// The x operand depends on forward data only: staged during the forward pass (where a training step leaves the GPU mostly idle
+// beside its one chain of kernels) into the workspace that the weight-gradient call of the backward pass receives with x == NULL.
+int conv_wgrad_tc_stage_x(const hmvae_conv_plan* plan, const float* x, int B, int T, void* workspace, long workspace_bytes,
+                          cudaStream_t st) {
+  WgArgs p;
+  if (!wg_geometry(plan, B, T, &p)) return fail_arg("conv_wgrad_stage_x (tcgen05): unsupported geometry");
+  if (!workspace || workspace_bytes < wg_dy_bytes(p) + wg_x_bytes(p) + wg_part_bytes(p) || !aligned16(workspace))
+    return fail_arg("conv_wgrad_stage_x (tcgen05): workspace too small or misaligned");
+  unsigned char* dyw = reinterpret_cast<unsigned char*>(workspace);
+  return wg_stage(p, x, nullptr, nullptr, dyw, dyw + wg_dy_bytes(p), 2, st);
+}
+
 int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* yact, float* dw,
                          float* dbias, int B, int T, int accumulate, void* workspace, long workspace_bytes,
                          cudaStream_t st) {
@@ -566,13 +592,7 @@ int conv_wgrad_tc_launch(const hmvae_conv_plan* plan, const float* x, const floa
   unsigned char* dyw = reinterpret_cast<unsigned char*>(workspace);
   unsigned char* xw = dyw + wg_dy_bytes(p);
   {
-    const long items = (wg_dy_bytes(p) + wg_x_bytes(p)) / 16;
-    // resident CTAs per SM: the staging pass runs beside the data-gradient chain; a full complement of 8 x 256 threads per SM
-    // leaves the chain's CTAs no thread slots until a staging CTA retires (tools/timeline.py)
-    long blocks = (items + 255) / 256, cap = (long)num_sms() * env_int("HMVAE_WG_PREP_CTAS_PER_SM", 8);
-    launch_pdl(conv_wgrad_prep_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p, x, dy, yact,
-               reinterpret_cast<float4*>(dyw), reinterpret_cast<float4*>(xw));
-    int rc = check_launch("conv_wgrad_prep");
+    int rc = wg_stage(p, x, dy, yact, dyw, xw, x ? 0 : 1, st);      // x == NULL: its tiles are already in the workspace
     if (rc) return rc;
   }
   if (dbias) {

@@ -362,6 +362,10 @@ class FusedDataParallelAdam:
         from . import ops
 
         table, n, live = self._live_ranges(select, written)
+        if getattr(self, "_tick_due", False):
+            _lib.check(_lib.lib.hmvae_opt_clock_tick(self._clock.data_ptr(), self.lr, self.gamma, self.step_size, self.betas[0],
+                                                     self.betas[1], _lib.ptr(self._dyn_dev), ops.stream()), "opt_clock_tick")
+            self._tick_due = False
         for i in live:
             torch.autograd.graph.increment_version(self.params[i])
         scale = (1.0 / self.world) if grad_scale is None else grad_scale
@@ -375,15 +379,10 @@ class FusedDataParallelAdam:
         been stepped yet."""
         from . import ops
 
-        # on the optimiser's side stream: only the optimiser kernels read the scalars, and the first kernels of a step are the
-        # forward pass's critical path
-        if getattr(self, "_opt_stream", None) is None:
-            self._opt_stream = torch.cuda.Stream()
-        self._opt_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._opt_stream):
-            _lib.check(_lib.lib.hmvae_opt_clock_tick(self._clock.data_ptr(), self.lr, self.gamma, self.step_size, self.betas[0],
-                                                     self.betas[1], _lib.ptr(self._dyn_dev), ops.stream()), "opt_clock_tick")
-        self._partial_pending = True           # step_dyn joins the side stream (the tick, and any partial step issued on it)
+        # The tick itself is issued lazily, on the optimiser's side stream right before the step's first optimiser kernel
+        # (_launch): only those kernels read its scalars, and as a dependency-free node at the head of a replayed graph it would
+        # be dispatched ahead of the forward pass's first kernels (tools/timeline.py).
+        self._tick_due = True
         self._stepped = set()
         self._begun = True
 

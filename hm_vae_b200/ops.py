@@ -90,6 +90,13 @@ def _eps_stream():
     return _overlap["eps"]
 
 
+def _prestage_stream():
+    """Stream of the weight gradients' x-operand staging issued during the forward pass (stack._prestage_x)."""
+    if _overlap.get("prestage") is None:
+        _overlap["prestage"] = torch.cuda.Stream(priority=0)
+    return _overlap["prestage"]
+
+
 def _wgrad_stream():
     """Weight gradients of consecutive layers go round-robin to HMVAE_WGRAD_STREAMS side streams.  Default 2: with the linked
     stack path the data-gradient chain is short enough that ONE stream of weight gradients (prep -> bias -> tcgen05 kernel per

@@ -301,8 +301,8 @@ class TwoHierSAVAEModel(nn.Module):
                 # path -- but they are ISSUED only after the encoder's kernels: a replayed CUDA graph hands its first nodes to
                 # the GPU one after the other (~2 us each, tools/timeline.py), and four generator kernels ahead of the first
                 # conv delayed it by as much.
-                fork = torch.cuda.Event()
-                fork.record()
+                fork = torch.cuda.Event()          # recorded below, after the step's first kernel: a dependency-free node at the
+                                                   # head of a replayed graph is dispatched ahead of the forward pass's kernels
 
                 def draw(_main=torch.cuda.current_stream()):
                     side = ops._eps_stream()
@@ -315,10 +315,13 @@ class TwoHierSAVAEModel(nn.Module):
                         t.record_stream(_main)
                     return e, ready
                 if os.environ.get("HMVAE_LATE_EPS", "1") == "0":
+                    fork.record()
                     (eps, eps_ready), draw = draw(), None
         late = {"eps": eps, "ready": eps_ready, "draw": draw}
         ops.prefetch_packs(self.enc.conv_plans() + self.dec.conv_plans())   # tf32 weight copies, on the side stream
         x = ops.transpose_ct(seq_rot_6d)                            # bs X (24*6) X T   (input is [B, T, C])
+        if late["draw"] is not None:
+            fork.record()
         # persistent accumulators: [sum sq 6d, sum sq rot, sum sq pos, unused, KL sum shallow, KL sum deep]; zeroed by finalize
         acc, res = self._loss_buffers(dev)
         split = self.mid_backward is not None and not validation_flag

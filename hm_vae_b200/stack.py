@@ -108,7 +108,35 @@ class _Geometry:
             self.t_out.append(t)
 
 
-def _wgrad(plan, x, gy, y, w, bias, b, t_in, want_w, want_b, inline=False):
+_prestage = os.environ.get("HMVAE_WGRAD_PRESTAGE", "1") != "0"
+
+
+def _prestage_x(plan, x, b, t_in, want, after=None):
+    """The x operand of conv ``plan``'s tensor-core weight gradient depends on forward data only: its TF32 tiles are staged NOW,
+    on a side stream beside the forward chain (which leaves most of the GPU idle), instead of inside the crowded backward pass.
+    ``after``: event recorded when ``x`` was complete (default: the current stream's position).  Returns the workspace the
+    weight-gradient call receives (with x = NULL), or None."""
+    if not (want and _prestage and ops._wgrad_tc and ops._overlap["allowed"] and lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in)):
+        return None
+    ps = ops._prestage_stream()
+    if after is not None:
+        ps.wait_event(after)
+    else:
+        ps.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(ps):
+        nbytes = int(lib.hmvae_conv_wgrad_tc_workspace(plan.handle, b, t_in))
+        ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
+        check(lib.hmvae_conv_wgrad_tc_stage_x(plan.handle, ptr(x), b, t_in, ptr(ws), ws.numel() * 4, stream()), "conv_wgrad_tc_stage_x")
+    return ws
+
+
+def _mark():
+    ev = torch.cuda.Event()
+    ev.record()
+    return ev
+
+
+def _wgrad(plan, x, gy, y, w, bias, b, t_in, want_w, want_b, inline=False, pre=None):
     """Weight / bias gradient of one conv on the side stream (inside ops.wgrad_overlap) -- same kernels as the per-layer path.
     ``inline``: on the caller's stream instead (the LAST weight gradient of a backward pass: nothing is left to overlap with, and
     round-robin would queue it behind an earlier layer's kernels on a side stream)."""
@@ -118,15 +146,20 @@ def _wgrad(plan, x, gy, y, w, bias, b, t_in, want_w, want_b, inline=False):
     if ops._overlap["on"] and not inline:
         side = ops._wgrad_stream()
         side.wait_stream(torch.cuda.current_stream())
+    if pre is not None:                                   # x tiles staged during the forward pass (_prestage_x)
+        (side if side is not None else torch.cuda.current_stream()).wait_stream(ops._prestage_stream())
     with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
         gb = ops.grad_buffer(bias.detach()) if (bias is not None and want_b) else None
         ws = None
-        if ops._wgrad_tc and lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in):
+        if pre is not None or (ops._wgrad_tc and lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in)):
             gw = ops.grad_buffer(w, zero=True)
-            n = int(lib.hmvae_conv_wgrad_tc_workspace(plan.handle, b, t_in))
-            ws = torch.empty((n + 3) // 4, device=x.device, dtype=torch.float32)
-            check(lib.hmvae_conv_wgrad_tc(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, ptr(ws), ws.numel() * 4,
-                                          stream()), "conv_wgrad_tc")
+            if pre is not None:
+                ws = pre
+            else:
+                n = int(lib.hmvae_conv_wgrad_tc_workspace(plan.handle, b, t_in))
+                ws = torch.empty((n + 3) // 4, device=x.device, dtype=torch.float32)
+            check(lib.hmvae_conv_wgrad_tc(plan.handle, None if pre is not None else ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0,
+                                          ptr(ws), ws.numel() * 4, stream()), "conv_wgrad_tc")
         else:
             gw = ops.grad_buffer(w)
             check(lib.hmvae_conv_wgrad(plan.handle, ptr(x), ptr(gy), ptr(y), ptr(gw), ptr(gb), b, t_in, 0, 0, stream()), "conv_wgrad")
@@ -155,6 +188,9 @@ class _DecoderStackFn(Function):
         packs = [None] * n                                   # each conv waits for ITS packed weights only (packing runs on the side stream)
         packs[0] = _packed(plans[0], ws[0])
         check(lib.hmvae_conv_tc_run(plans[0].handle, 0, ptr(packs[0][0]), b, geo.t_in[0], ptr(st), ptr(dump), stream()), "conv_tc_run")
+        pre = [None] * n                                     # weight-gradient x tiles, staged beside the forward chain
+        if spec_grad:
+            pre[0] = _prestage_x(plans[0], feat0, b, geo.t_in[0], ctx.needs_input_grad[3])
         for i in range(1, n + 1):
             prod = plans[i - 1]
             cons = plans[i] if i < n else None
@@ -169,10 +205,14 @@ class _DecoderStackFn(Function):
                   act=prod.lrelu, dump=dump, bias=bs[i - 1], aux=aux, s_out=s_i, stage_ws=st_c if cons is not None else None)
             bounds.append(s_i)
             if cons is not None:
+                ready = _mark() if (spec_grad and _prestage and ctx.needs_input_grad[3 + i]) else None
                 packs[i] = _packed(cons, ws[i])
                 check(lib.hmvae_conv_tc_run(cons.handle, 0, ptr(packs[i][0]), b, geo.t_in[i], ptr(st_c), ptr(dump_c), stream()), "conv_tc_run")
                 dump = dump_c
+                if ready is not None:                        # issued after the chain's kernel: issue order = dispatch order
+                    pre[i] = _prestage_x(cons, s_i, b, geo.t_in[i], True, after=ready)
         if spec_grad:
+            ctx.wg_pre = pre
             ctx.spec, ctx.b, ctx.concat = spec, b, concat
             ctx.packs_d = [p[1] for p in packs]
             ctx.has_bias = [x is not None for x in bs]
@@ -185,6 +225,8 @@ class _DecoderStackFn(Function):
         plans, geo = spec["plans"], spec["geo"]
         n = len(plans)
         if gout is None:
+            if any(w is not None for w in ctx.wg_pre):
+                torch.cuda.current_stream().wait_stream(ops._prestage_stream())
             return (None,) * (3 + 2 * n)
         saved = ctx.saved_tensors
         bounds, ws = saved[:n + 1], saved[n + 1:2 * n + 1]
@@ -202,8 +244,9 @@ class _DecoderStackFn(Function):
         # replayed graph that become ready together are dispatched in issue order, and the staging pass of this weight gradient
         # fills every SM's thread slots for ~30 us (tools/timeline.py: the first dgrad kernel started 10 us late behind it)
         chain = need_x or any(need_w[:-1]) or any(need_b[:-1])
+        pre = ctx.wg_pre
         first = lambda: _wgrad(plans[n - 1], bounds[n - 1], gout, bounds[n] if plans[n - 1].lrelu else None, ws[n - 1], bs[n - 1],
-                               b, geo.t_in[n - 1], need_w[n - 1], need_b[n - 1])
+                               b, geo.t_in[n - 1], need_w[n - 1], need_b[n - 1], pre=pre[n - 1])
         if not (chain and _wgrad_after_dgrad):
             gws[n - 1], gbs[n - 1] = first()
         if chain:
@@ -229,7 +272,7 @@ class _DecoderStackFn(Function):
                           "conv_tc_run")
                     dump = dump_c
                     gws[i - 1], gbs[i - 1] = _wgrad(cons, bounds[i - 1], g_i, bounds[i] if cons.lrelu else None, ws[i - 1], bs[i - 1], b,
-                                                    geo.t_in[i - 1], need_w[i - 1], need_b[i - 1])
+                                                    geo.t_in[i - 1], need_w[i - 1], need_b[i - 1], pre=pre[i - 1])
         gfeat0 = gbounds[0]
         gfeat_last = None
         if ctx.concat and gbounds[n - 1] is not None:
@@ -314,6 +357,9 @@ class _EncoderStackFn(Function):
         packs = [None] * n                                   # each conv waits for ITS packed weights only (packing runs on the side stream)
         packs[0] = _packed(plans[0], ws[0])
         check(lib.hmvae_conv_tc_run(plans[0].handle, 0, ptr(packs[0][0]), b, geo.t_in[0], ptr(st), ptr(dump), stream()), "conv_tc_run")
+        pre = [None] * n                                     # weight-gradient x tiles, staged beside the forward chain
+        if spec_grad:
+            pre[0] = _prestage_x(plans[0], x, b, geo.t_in[0], ctx.needs_input_grad[2])
         for i in range(1, n + 1):
             prod = plans[i - 1]
             cons = plans[i] if i < n else None
@@ -327,10 +373,14 @@ class _EncoderStackFn(Function):
                   pool=pool, dump=dump, bias=bs[i - 1], s_out=s_i, stage_ws=st_c if cons is not None else None)
             bounds.append(s_i)
             if cons is not None:
+                ready = _mark() if (spec_grad and _prestage and ctx.needs_input_grad[2 + i]) else None
                 packs[i] = _packed(cons, ws[i])
                 check(lib.hmvae_conv_tc_run(cons.handle, 0, ptr(packs[i][0]), b, geo.t_in[i], ptr(st_c), ptr(dump_c), stream()), "conv_tc_run")
                 dump = dump_c
+                if ready is not None:
+                    pre[i] = _prestage_x(cons, s_i, b, geo.t_in[i], True, after=ready)
         if spec_grad:
+            ctx.wg_pre = pre
             ctx.spec, ctx.b = spec, b
             ctx.packs_d = [p[1] for p in packs]
             ctx.has_bias = [v is not None for v in bs]
@@ -353,6 +403,9 @@ class _EncoderStackFn(Function):
         if ctx.needs_input_grad[1]:
             raise _lib.HmvaeError("encoder stack: gradient w.r.t. the network input is not implemented on the stack path")
         live = [i for i in range(n) if gs[i] is not None]
+        top = live[-1] if live else -1
+        if any(w is not None for w in ctx.wg_pre[top + 1:]):      # pre-staged tiles nobody will consume: re-join their stream
+            torch.cuda.current_stream().wait_stream(ops._prestage_stream())
         if not live:
             return (None, None) + tuple(gws) + tuple(gbs)
         # Notation: R_i = raw output of conv i, bounds[i+1] = LeakyReLU(pool_i(R_i)).  The chain starts at the deepest conv whose
@@ -374,7 +427,7 @@ class _EncoderStackFn(Function):
 
             def wgrad_i(i=i, plan=plan, gy=gy, yact=yact):
                 gws[i], gbs[i] = _wgrad(plan, bounds[i], gy, yact, ws[i], bs[i], b, geo.t_in[i], need_w[i], need_b[i],
-                                        inline=(i == 0 and _last_inline))
+                                        inline=(i == 0 and _last_inline), pre=ctx.wg_pre[i])
                 if spec.get("hook") is not None:
                     spec["hook"](i, n)                     # e.g. the optimiser's bucket for this level (Trainer, split step)
             if i == 0 or not _wgrad_after_dgrad:

@@ -23,6 +23,8 @@
  *   hmvae_adam_step         trainer_motion_vae.py:29-31, 92-93  torch.optim.Adam(lr, weight_decay) step
  *   hmvae_dp_adam_step      train_motion_vae.py:49-53 (nn.DataParallel) + trainer_motion_vae.py:29-31, 92-93: gradient
  *                           reduce-scatter + Adam + parameter all-gather over NVLink peer memory, one kernel per rank
+ *   hmvae_dp_adam_step_units  the same step over a device table of work units that leaves out the always-masked blocks of the
+ *                           SkeletonConv weights (skeleton.py:84-96: zero value, zero gradient)
  *   hmvae_linear_*          seq_two_hier_sa_vae.py:132-136, 159-164, 225-229, 267  latent nn.Linear heads
  *   hmvae_batch_assemble,   utils_motion_vae.py:140-187 (MotionSeqData.__getitem__ arithmetic) and :17-57
  *   hmvae_rand_rotation     (rand_rotation_matrix): the batch assembly right before the path
@@ -160,6 +162,11 @@ int hmvae_conv_wgrad_tc_supported(const hmvae_conv_plan* plan, int batch, int t_
 long hmvae_conv_wgrad_tc_workspace(const hmvae_conv_plan* plan, int batch, int t_in);
 int hmvae_conv_wgrad_tc(const hmvae_conv_plan* plan, const float* x, const float* dy, const float* y, float* dw, float* dbias,
                         int batch, int t_in, int accumulate, void* workspace, long workspace_bytes, void* stream);
+/* The x operand of the weight gradient (the conv's source tensor, skeleton.py:95-105's `input`) depends on forward data only:
+ * this stages its TF32 tiles into `workspace` ahead of time (during the forward pass); the backward pass then calls
+ * hmvae_conv_wgrad_tc with x == NULL and the SAME workspace, and only dy is staged there. */
+int hmvae_conv_wgrad_tc_stage_x(const hmvae_conv_plan* plan, const float* x, int batch, int t_in, void* workspace,
+                                long workspace_bytes, void* stream);
 
 /* adjoint of the prologue: dsrc[B, src_joints*ci, T_src] from dxin[B, J*ci, T]; if src_act != NULL the result is
  * multiplied by lrelu'(src_act) (src_act = the activation tensor that fed this layer). */

@@ -272,6 +272,46 @@ def test_conv_layer_shapes_b512(golden_topology, shape):
     _conv_layer_case(golden_topology, shape, "auto", 512)
 
 
+@pytest.mark.parametrize("shape", LAYER_SHAPES)
+def test_conv_wgrad_prestaged_x_is_bit_identical(golden_topology, shape):
+    """hmvae_conv_wgrad_tc_stage_x (x tiles staged ahead of time, as the stack path does during the forward pass) followed by
+    hmvae_conv_wgrad_tc with x = NULL writes exactly what the one-call form writes: dW and dbias, every layer geometry."""
+    from hm_vae_b200._lib import lib, check, ptr
+    lvl, ci, co, k, s_, t_in, up, unpool_lvl = shape
+    b = 32 if k == 15 else 8
+    topo = golden_topology["levels"]
+    nb = topo[lvl]["neighbours"]
+    j = len(nb)
+    torch.manual_seed(5 + lvl)
+    conv = H.SkeletonConv(nb, j * ci, j * co, k, j, stride=s_, padding=(k - 1) // 2, bias=True, padding_mode="reflection").to(DEV)
+    if unpool_lvl is not None:
+        pl = topo[unpool_lvl]["pooling_list"]
+        un = H.SkeletonUnpool(pl, ci)
+        plan = conv.plan(upsample=True, unpool_src=un.src, src_joints=len(pl), lrelu=True)
+        x = torch.randn(b, len(pl) * ci, t_in // 2, device=DEV)
+    else:
+        plan = conv.plan(lrelu=True)
+        x = torch.randn(b, j * ci, t_in, device=DEV)
+    if not lib.hmvae_conv_wgrad_tc_supported(plan.handle, b, t_in):
+        pytest.skip("tensor-core weight gradient does not cover this geometry")
+    t_out = (t_in + 2 * ((k - 1) // 2) - k) // s_ + 1
+    dy = torch.randn(b, j * co, t_out, device=DEV)
+    yact = torch.randn(b, j * co, t_out, device=DEV)
+    n = int(lib.hmvae_conv_wgrad_tc_workspace(plan.handle, b, t_in))
+    outs = []
+    for pre in (False, True):
+        ws = torch.full(((n + 3) // 4,), float("nan"), device=DEV)
+        gw, gb = torch.zeros_like(conv.weight), torch.zeros_like(conv.bias)
+        if pre:
+            check(lib.hmvae_conv_wgrad_tc_stage_x(plan.handle, ptr(x), b, t_in, ptr(ws), ws.numel() * 4, None), "stage_x")
+        check(lib.hmvae_conv_wgrad_tc(plan.handle, None if pre else ptr(x), ptr(dy), ptr(yact), ptr(gw), ptr(gb), b, t_in, 0, ptr(ws),
+                                      ws.numel() * 4, None), "wgrad_tc")
+        torch.cuda.synchronize()
+        outs.append((gw.cpu(), gb.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert float(outs[0][0].abs().sum()) > 0 and not torch.isnan(outs[0][0]).any()
+
+
 def test_conv_reflect_pad_too_large_is_an_error(golden_topology):
     nb = golden_topology["levels"][3]["neighbours"]
     conv = H.SkeletonConv(nb, 7 * 2, 7 * 2, 15, 7, padding=7, padding_mode="reflection").to(DEV)
