@@ -406,8 +406,11 @@ class FusedDataParallelAdam:
         for s in ops._overlap.get("used", ()) or ():           # weight gradients are produced on the side stream(s)
             self._opt_stream.wait_stream(s)
         with torch.cuda.stream(self._opt_stream):
-            self._launch(select, grad_scale, max_ctas=int(os.environ.get("HMVAE_DP_PARTIAL_CTAS", "296")),
-                         in_flight=int(os.environ.get("HMVAE_DP_PARTIAL_IN_FLIGHT", "0")), written=written)
+            # across ranks: a small grid that hides the NVLink latency with loads in flight instead of threads, so that the
+            # bucket does not take the SMs of the backward pass it runs under (8 GPUs: 32 CTAs x 4 beat 64 x 2 and the full grid)
+            multi = self.world > 1
+            self._launch(select, grad_scale, max_ctas=int(os.environ.get("HMVAE_DP_PARTIAL_CTAS", "32" if multi else "296")),
+                         in_flight=int(os.environ.get("HMVAE_DP_PARTIAL_IN_FLIGHT", "4" if multi else "0")), written=written)
         self._stepped.update(select)
         self._partial_pending = True
 

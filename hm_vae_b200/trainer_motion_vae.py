@@ -117,12 +117,18 @@ class Trainer(nn.Module):
                     self._configure_schedule()
                     self._sync = _NoCollective(world)
                     self.dp_mode = "fused_peer_memory(%s)" % self.gen_opt.arenas.backend
-                    # The decoder's share of the optimiser step starts as soon as the decoder's gradients are final and runs under
-                    # the encoder's backward.  Measured: 1 GPU 0.910 -> 0.890 ms per step; 2 GPUs 0.955 -> 1.006 (the early
-                    # kernel waits for its peers while sitting on SMs the encoder backward wants) => on by default only for 1 rank.
+                    # Buckets in reverse-layer order: the decoder's share of the optimiser step (and of the collective) starts as
+                    # soon as the decoder's gradients are final and runs under the encoder's backward.  Measured (ms per step,
+                    # graph replay, A/B inside one box): 1 GPU 0.754 -> 0.742 with a second bucket for the deepest encoder level;
+                    # 8 GPUs on the NVSwitch multicast path 0.861 -> 0.831 with the decoder bucket on 32 CTAs x 4 loads in flight
+                    # (a second bucket there: 0.910 -- its flag barrier lands where the encoder backward has no slack);
+                    # 2 GPUs (unicast peer loads, 4x the bytes per rank) 0.768 -> 0.805: off.  profiles/r02_dp_overlap_ab_*.log
                     dec = getattr(self.model, "dec", None)
                     split = os.environ.get("HMVAE_DP_SPLIT", "auto")
-                    if dec is not None and (world == 1 if split == "auto" else split != "0"):
+                    # across ranks only where a rank's share of the bucket is small enough to fit the window: 8 ranks on the
+                    # multicast path (4 ranks, same settings: 0.844 -> 0.886 ms, off)
+                    nvls = bool(self.gen_opt.arenas.mc_grad) and world >= int(os.environ.get("HMVAE_DP_SPLIT_MIN_WORLD", "8"))
+                    if dec is not None and ((world == 1 or nvls) if split == "auto" else split != "0"):
                         enc_ids = {id(p) for p in self.model.enc.parameters()}
                         dec_ids = {id(p) for p in dec.parameters()} - enc_ids
                         self.model.mid_backward = lambda: self.gen_opt.step_partial(dec_ids, grad_scale=1.0 / world)
@@ -130,7 +136,8 @@ class Trainer(nn.Module):
                         # second bucket (reverse-layer order): the deepest encoder conv -- a quarter of the arena at len64 -- and
                         # the encoder's latent heads, as soon as that level's weight-gradient kernels have been issued; the
                         # step's tail then only covers the shallow encoder levels
-                        if os.environ.get("HMVAE_DP_SPLIT_ENC", "1") != "0" and hasattr(self.model.enc, "convs"):
+                        enc_bucket = os.environ.get("HMVAE_DP_SPLIT_ENC", "auto")
+                        if (world == 1 if enc_bucket == "auto" else enc_bucket != "0") and hasattr(self.model.enc, "convs"):
                             import weakref
                             from . import stack
                             convs = list(self.model.enc.convs)
