@@ -109,6 +109,8 @@ class _Geometry:
 
 
 _prestage = os.environ.get("HMVAE_WGRAD_PRESTAGE", "1") != "0"
+# under no_grad the boundary tensors between two convs that nobody reads are not written (the link kernel only stages the consumer)
+_skip_bounds = os.environ.get("HMVAE_STACK_SKIP_BOUNDS", "1") != "0"
 
 
 def _prestage_x(plan, x, b, t_in, want, after=None):
@@ -181,7 +183,8 @@ class _DecoderStackFn(Function):
         if concat:
             feat_last = feat_last.contiguous()
         dev = feat0.device
-        spec_grad = any(ctx.needs_input_grad)
+        # ctx.needs_input_grad mirrors requires_grad of the inputs whatever the grad mode: the caller's grad mode rides in the spec
+        spec_grad = spec["grad"] and any(ctx.needs_input_grad)
         bounds = [feat0]                                     # bounds[i] = source tensor of conv i
         st, dump = _bufs(plans[0], 0, b, geo.t_in[0])
         check(lib.hmvae_conv_tc_stage(plans[0].handle, 0, ptr(feat0), None, b, geo.t_in[0], ptr(st), stream()), "conv_tc_stage")
@@ -196,7 +199,7 @@ class _DecoderStackFn(Function):
             cons = plans[i] if i < n else None
             chans = prod.joints * prod.out_joint_stride
             # interior boundary tensors are only needed again by the backward pass: not written under no_grad
-            keep = cons is None or spec_grad
+            keep = cons is None or spec_grad or not _skip_bounds
             s_i = torch.empty((b, chans, geo.t_out[i - 1]), device=dev, dtype=torch.float32) if keep else None
             aux = feat_last if (concat and i == n - 1) else None
             if cons is not None:
@@ -329,7 +332,7 @@ def decoder_forward(dec, feat0, feat_last):
     _last_plans[dec] = spec["plans"]
     ws = [c.weight for c in dec.convs]
     bs = [c.bias for c in dec.convs]
-    return _DecoderStackFn.apply(spec, feat0, feat_last, *ws, *bs)
+    return _DecoderStackFn.apply(dict(spec, grad=torch.is_grad_enabled()), feat0, feat_last, *ws, *bs)
 
 
 # ======================================================================================================== encoder
@@ -350,7 +353,7 @@ class _EncoderStackFn(Function):
         ws, bs = params[:n], params[n:]
         x = x.contiguous()
         dev = x.device
-        spec_grad = any(ctx.needs_input_grad)
+        spec_grad = spec["grad"] and any(ctx.needs_input_grad)
         bounds = [x]
         st, dump = _bufs(plans[0], 0, b, geo.t_in[0])
         check(lib.hmvae_conv_tc_stage(plans[0].handle, 0, ptr(x), None, b, geo.t_in[0], ptr(st), stream()), "conv_tc_stage")
@@ -365,7 +368,7 @@ class _EncoderStackFn(Function):
             cons = plans[i] if i < n else None
             pool = pools[i - 1]
             e_out = len(pool) if pool is not None else prod.joints
-            keep = cons is None or spec_grad or (i - 1) in spec["needed"]
+            keep = cons is None or spec_grad or (i - 1) in spec["needed"] or not _skip_bounds
             s_i = torch.empty((b, e_out * prod.co, geo.t_out[i - 1]), device=dev, dtype=torch.float32) if keep else None
             if cons is not None:
                 st_c, dump_c = _bufs(cons, 0, b, geo.t_in[i])
@@ -493,7 +496,8 @@ def encoder_forward(enc, x, needed=None):
     spec = encoder_spec(enc, x.shape[0], x.shape[2])
     if spec is None:
         return None
-    spec = dict(spec, needed=set(range(len(enc.convs))) if needed is None else set(needed), hook=wgrad_issued_hooks.get(enc))
+    spec = dict(spec, needed=set(range(len(enc.convs))) if needed is None else set(needed), hook=wgrad_issued_hooks.get(enc),
+                grad=torch.is_grad_enabled())
     ws = [c.weight for c in enc.convs]
     bs = [c.bias for c in enc.convs]
     return _EncoderStackFn.apply(spec, x, *ws, *bs)
