@@ -163,7 +163,7 @@ def _dp_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from hm_vae_b200.dp_fused import arena_layout, owned_ranges
+        from hm_vae_b200.dp_fused import arena_layout
 
         # the reduce-scatter / sharded-Adam / all-gather dataflow of hmvae_dp_adam_step, emulated with gloo collectives on the
         # host: every rank updates only its owned ranges from the SUM of all ranks' gradients, then the ranks exchange their
@@ -178,16 +178,34 @@ def _dp_worker(rank, world, port, out):
         torch.manual_seed(10 + rank)
         for p, o in zip(params, offs):
             g_arena[o:o + p.numel()] = torch.randn(p.numel())
-        live = [(o, o + (p.numel() + 3) // 4 * 4) for p, o in zip(params, offs)]
+        # tensor 0 is a masked SkeletonConv-style weight: dead entries hold zero values and zero gradients and are in no work unit
+        from hm_vae_b200.dp_fused import balanced_bounds, clip_ranges, cut_units, mask_live_ranges
+        mask0 = torch.zeros(shapes[0])
+        mask0[:3, :2] = 1
+        mask0[3:, 2:] = 1
+        dead0 = (mask0 == 0).reshape(-1)
+        p_arena[offs[0]:offs[0] + mask0.numel()][dead0] = 0
+        g_arena[offs[0]:offs[0] + mask0.numel()][dead0] = 0
+        params[0] = params[0] * mask0
+        plive = [mask_live_ranges(mask0.numpy(), offs[0])] + [[(o, o + (p.numel() + 3) // 4 * 4)] for p, o in zip(params[1:], offs[1:])]
+        live = [r for rs in plive for r in rs]
+        bounds = balanced_bounds(live, world, total)                 # static shares, balanced on the live elements
         gsum = g_arena.clone()
         dist.all_reduce(gsum)                                        # what the peer loads add up to
         lr, b1, b2, eps, wd = 1e-2, 0.9, 0.999, 1e-8, 1e-4
         new = torch.zeros(total)
-        for b, e in owned_ranges(live, rank, world, total):
+        touched = torch.zeros(total)
+        for first4, n4 in cut_units(clip_ranges(live, bounds[rank], bounds[rank + 1])).tolist():      # this rank's unit table
+            b, e = 4 * first4, 4 * (first4 + n4)
             g = gsum[b:e] / world + wd * p_arena[b:e]
             m, v = (1 - b1) * g, (1 - b2) * g * g
             new[b:e] = p_arena[b:e] - lr / (1 - b1) * m / (v.sqrt() / (1 - b2) ** 0.5 + eps)
+            touched[b:e] += 1
         dist.all_reduce(new)                                         # shares are disjoint: the sum is the all-gather
+        dist.all_reduce(touched)
+        assert float(touched.max()) == 1.0                           # every element stepped by at most one rank ...
+        t0 = touched[offs[0]:offs[0] + mask0.numel()]
+        assert bool((t0[~dead0] == 1).all()) and float(t0[dead0].sum()) < 0.5 * float(dead0.sum())    # ... live ones exactly once
         ref_p = [p.clone().requires_grad_(True) for p in params]
         opt = torch.optim.Adam(ref_p, lr=lr, weight_decay=wd)
         for p, o in zip(ref_p, offs):
