@@ -8,7 +8,8 @@ gradient kernels write straight into the gradient arena (``ops.grad_buffer``), s
 reduce-scatter -> sharded Adam -> all-gather; there is no NCCL call on the step path and the whole step, collective
 included, is one CUDA graph.
 
-The pure-Python helpers (``arena_layout``, ``merge_ranges``, ``owned_ranges``) are covered by the CPU tests (gloo, world 2).
+The pure-Python helpers (``arena_layout``, ``merge_ranges``, ``mask_live_ranges``, ``balanced_bounds``, ``clip_ranges``,
+``cut_units``) are covered by the CPU tests (gloo, world 2).
 """
 import ctypes
 import os
@@ -41,24 +42,6 @@ def merge_ranges(ranges):
         else:
             out.append([b, e])
     return [tuple(r) for r in out]
-
-
-def rank_share(total, rank, world):
-    """Static ownership: rank r owns arena elements [lo, hi) -- independent of which parameters are live in a given step, so
-    a rank's slice of the Adam moments never migrates."""
-    units = total // ALIGN
-    return (units * rank) // world * ALIGN, (units * (rank + 1)) // world * ALIGN
-
-
-def owned_ranges(live, rank, world, total):
-    """Live element ranges intersected with the rank's static share.  Over all ranks: disjoint, union == live."""
-    lo, hi = rank_share(total, rank, world)
-    out = []
-    for b, e in merge_ranges(live):
-        s, t = max(b, lo), min(e, hi)
-        if t > s:
-            out.append((s, t))
-    return out
 
 
 UNIT = 32          # float4 per work unit of hmvae_dp_adam_step_units (one per lane of a warp)

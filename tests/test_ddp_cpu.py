@@ -91,22 +91,22 @@ def test_bucket_order_is_reverse_of_registration():
 
 # ------------------------------------------------------------------------------------------------ fused DP optimiser (host logic)
 def test_arena_layout_and_static_ownership():
-    from hm_vae_b200.dp_fused import ALIGN, arena_layout, merge_ranges, owned_ranges, rank_share
+    from hm_vae_b200.dp_fused import ALIGN, arena_layout, balanced_bounds, clip_ranges, merge_ranges
 
     numels = [288 * 144 * 15, 288, 24 * 384, 24, 3, 1008, 7]
     offs, total = arena_layout(numels)
     assert all(o % ALIGN == 0 for o in offs) and total % ALIGN == 0
     assert all(offs[i + 1] >= offs[i] + numels[i] for i in range(len(numels) - 1)) and total >= offs[-1] + numels[-1]
-    live = [(offs[i], offs[i] + (numels[i] + ALIGN - 1) // ALIGN * ALIGN) for i in (0, 1, 4, 6)]      # params 2, 3, 5 are dead
+    every = [(offs[i], offs[i] + (numels[i] + ALIGN - 1) // ALIGN * ALIGN) for i in range(len(numels))]
+    live = [every[i] for i in (0, 1, 4, 6)]                                     # params 2, 3, 5 got no gradient this step
     assert merge_ranges([(8, 12), (0, 4), (4, 8), (20, 24)]) == [(0, 12), (20, 24)]
     for world in (1, 2, 3, 8):
-        shares = [rank_share(total, r, world) for r in range(world)]
-        assert shares[0][0] == 0 and shares[-1][1] == total
-        assert all(shares[r][1] == shares[r + 1][0] for r in range(world - 1))
+        bounds = balanced_bounds(every, world, total)                            # static: from ALL parameters, not the step's live set
+        assert bounds[0] == 0 and bounds[-1] == total and all(bounds[r] <= bounds[r + 1] for r in range(world))
         covered = []
         for r in range(world):
-            own = owned_ranges(live, r, world, total)
-            assert all(b % ALIGN == 0 and e % ALIGN == 0 and shares[r][0] <= b < e <= shares[r][1] for b, e in own)
+            own = clip_ranges(live, bounds[r], bounds[r + 1])
+            assert all(b % ALIGN == 0 and e % ALIGN == 0 and bounds[r] <= b < e <= bounds[r + 1] for b, e in own)
             covered += own
         assert merge_ranges(covered) == merge_ranges(live)                       # union == live ...
         assert sum(e - b for b, e in covered) == sum(e - b for b, e in merge_ranges(live))   # ... and disjoint
