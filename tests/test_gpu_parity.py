@@ -571,6 +571,38 @@ def test_dp_adam_kernel_vs_torch_single_rank():
     ops.unregister_grad_buffers()
 
 
+def test_dp_adam_host_range_entry_point_vs_torch():
+    """hmvae_dp_adam_step (HOST ranges instead of a device unit table; world == 1) straight through the C ABI: two ranges with a
+    gap that must stay untouched, against torch.optim.Adam."""
+    import ctypes
+    from hm_vae_b200 import _lib
+
+    n = 4 * 1000
+    gen = torch.Generator().manual_seed(3)
+    p0, g = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
+    param, grad = p0.clone().to(DEV), g.clone().to(DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    state = torch.zeros(4, dtype=torch.int32, device=DEV)
+    lr, b1, b2, eps, wd = 1e-3, 0.9, 0.999, 1e-8, 1e-2
+    dyn = torch.tensor([lr / (1 - b1), 1.0 / (1 - b2) ** 0.5], device=DEV)            # step 1: lr / bc1, 1 / sqrt(bc2)
+    peers = _lib.DpPeers()
+    peers.world, peers.rank = 1, 0
+    peers.grad[0], peers.param[0], peers.flags[0] = grad.data_ptr(), param.data_ptr(), state.data_ptr()
+    ranges = (ctypes.c_long * 4)(0, 1200, 2000, n)                                       # [1200, 2000) is not owned / not live
+    _lib.check(_lib.lib.hmvae_dp_adam_step(ctypes.byref(peers), _lib.ptr(m), _lib.ptr(v), ranges, 2, _lib.ptr(dyn), b1, b2, eps, wd,
+                                           1.0, state.data_ptr(), 0, None), "dp_adam_step")
+    torch.cuda.synchronize()
+    ref = p0.clone().requires_grad_(True)
+    ref.grad = g.clone()
+    torch.optim.Adam([ref], lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd).step()
+    got = param.cpu()
+    live = torch.ones(n, dtype=torch.bool)
+    live[1200:2000] = False
+    np.testing.assert_allclose(got[live].numpy(), ref.detach()[live].numpy(), rtol=1e-5, atol=1e-7)
+    assert torch.equal(got[~live], p0[~live]) and float(m.cpu()[~live].abs().max()) == 0.0
+    assert int(state[0]) == 1 and int(state[2]) == 0                                      # one completed call, no timeout
+
+
 def test_dp_adam_mask_aware_units_vs_torch():
     """The mask-aware unit table (hmvae_dp_adam_step_units): structurally dead entries of a SkeletonConv-style
     weight are left out of the sweep.  Against torch.optim.Adam with weight decay on the dense tensors: identical parameters and
